@@ -144,6 +144,26 @@ class DiscreteDiffusion:
                                     _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
         return hist, packed
 
+    def sample_to_host(self, basis_ids_host: torch.Tensor, n_shots: int, out_packed_host: torch.Tensor | None,
+                       out_hist_host: torch.Tensor | None, shot_offset: int = 0):
+        """End-to-end form with HOST buffers (ddqst_sample_host): basis ids are copied in, the packed bitstrings
+        and/or the per-basis counts are copied out (pinned memory recommended) and the stream is synchronised --
+        what the reference's ``p_sample(...).cpu().numpy()`` loop does per basis (RQC/evaluate.py:82-84)."""
+        self._require_cuda()
+        lib = _lib.load()
+        m = self.model
+        N = m.num_qubits
+        nb = basis_ids_host.numel()
+        if basis_ids_host.dtype != torch.int32 or basis_ids_host.is_cuda:
+            raise ValueError("basis_ids_host must be a host int32 tensor")
+        need = 4 * nb + (nb << N) * 4 + nb * n_shots * (1 if N <= 8 else 2) + 4096 + \
+            lib.ddqst_workspace_bytes(_lib.OP_SAMPLE, C.byref(m.dims), nb * n_shots, self._prec())
+        scratch = _lib.workspace.get(need, self.device)
+        hp = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        _lib.check(lib.ddqst_sample_host(C.byref(m.dims), _lib.ptr(m.packed()), _lib.ptr(self._sched), self.mode, self._prec(),
+                                         hp(basis_ids_host), nb, n_shots, shot_offset, self.seed, hp(out_packed_host),
+                                         hp(out_hist_host), _lib.ptr(scratch), scratch.numel(), _lib.stream_ptr()))
+
     @torch.no_grad()
     def p_sample(self, num_samples: int, basis_idx: int, num_qubits: int, shot_offset: int = 0):
         """-> x_0[num_samples, N] int64 on ``device`` (RQC/diffusion.py:53-80 / SS/diffusion.py:54-82)."""
