@@ -53,6 +53,7 @@ SIGNATURES = {
     "ddqst_sample_host": (C.c_int, [_DP, _P, _P, C.c_int, C.c_int, _P, _I32, _I64, _I64, _U64, _P, _P, _P, _I64, _P]),
     "ddqst_selftest_philox": (C.c_int, [_P, _I64, _P, _P]),
     "ddqst_selftest_umma": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
+    "ddqst_selftest_umma2": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
     "ddqst_debug_tc_status": (C.c_int, []),
 }
 

@@ -17,6 +17,7 @@
 // Warp roles (576 threads): warps 0-15 epilogue/compute (warp w owns TMEM lanes 32*(w%4).. and hidden
 // columns [(w/4)*H/4, ...)), warp 16 TMA producer, warp 17 MMA issuer + TMEM allocator.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "sampler_tc.cuh"
 #include "simt.cuh"
@@ -69,6 +70,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast form: the box lands at the same CTA-relative offset, and completes the same-offset mbarrier, in
+// every CTA of the cluster named by cta_mask
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -112,6 +132,54 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+
+// ---- cta_group::2 (CTA pair) forms.  Bit 24 of a shared::cluster address selects the CTA inside the pair;
+// clearing it names the leader's (even CTA's) copy of the same offset.
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
+}
+// arrive (release, cluster scope) on the leader CTA's copy of a barrier
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int code) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  long long start = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0) {
+      if (*((volatile int*)&g_tc_abort) != 0) return;
+      if (clock64() - start > 2000000000LL) { atomicCAS(&g_tc_abort, 0, code); return; }
+    }
+  }
+}
+__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16_m(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 __device__ __forceinline__ float silu_fast(float v) {
   float h = 0.5f * v, th;
   asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
@@ -132,7 +200,7 @@ __device__ __forceinline__ uint32_t a_chunk_off(int kb, int m, int chunk) {
 
 // ------------------------------------------------------------------------------------ kernel
 constexpr int kEpiThreads = 512;
-constexpr int kThreads = 576;
+constexpr int kThreads = 640;          // 16 epilogue warps + one producer warpgroup (TMA, MMA, 2 idle)
 constexpr int kStages = 4;
 constexpr int kStageBytes = 16384;
 
@@ -150,6 +218,7 @@ struct TcParams {
   uint32_t* out_hist;
   float* logits_out;                  // optional [rows, 2N] of the last executed step
   int64_t tiles_per_basis, n_tiles;
+  int32_t iters;                      // tile iterations per CTA (uniform so clustered CTAs stay in lock step)
 };
 
 template <int H>
@@ -169,7 +238,7 @@ __host__ __device__ constexpr int tc_smem_bytes(int L) {
          2 * L * H * 4 /*b1,b2*/ + 256 /*barriers*/;
 }
 
-template <int H>
+template <int H, int CS>
 __global__ void __launch_bounds__(kThreads, 1)
 sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_dt,
                   const __grid_constant__ CUtensorMap map_head, const TcParams P) {
@@ -191,9 +260,13 @@ sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = P.L, N = P.N;
   const int n_steps = P.t_start - P.t_end + 1;
+  // cluster of CS CTAs: every weight tile is fetched once per cluster (each CTA loads 1/CS of its rows and
+  // multicasts it), so a ring slot is free only when ALL CTAs of the cluster have consumed it
+  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
 
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, CS); }
     mbar_init(bar_acc, 1);
     mbar_init(bar_a, kEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -207,9 +280,12 @@ sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();        // peers' barriers are initialised before anything remote touches them
   tc_fence_after();
   const uint32_t tmem_base = *((volatile uint32_t*)tmem_slot);
 
+  if (warp >= 16) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 16) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
@@ -222,22 +298,31 @@ sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
         ++cnt;
         return s;
       };
-      for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      constexpr int SL = C::NT / CS;                                 // rows of each tile this CTA fetches
+      auto load_slice = [&](const CUtensorMap* map, uint32_t s, int col, int row) {
+        uint32_t dst = smem_u32(sRing + s * kStageBytes) + crank * SL * 128;
+        if (CS > 1) tma_load_2d_mc(dst, map, bar_full + 8 * s, col, row + (int)crank * SL, kMask);
+        else tma_load_2d(dst, map, bar_full + 8 * s, col, row);
+      };
+      for (int it = 0; it < P.iters; ++it) {
         for (int st = 0; st < n_steps; ++st) {
           for (int nc = 0; nc < C::NC; ++nc) {                       // input table
             uint32_t s = acquire(C::STAGE_TX);
-            tma_load_2d(smem_u32(sRing + s * kStageBytes), &map_dt, bar_full + 8 * s, 0, nc * C::NT);
+            load_slice(&map_dt, s, 0, nc * C::NT);
           }
           for (int g = 0; g < 2 * L; ++g)                            // W1, W2 of every block
             for (int nc = 0; nc < C::NC; ++nc)
               for (int kb = 0; kb < C::KB; ++kb) {
                 uint32_t s = acquire(C::STAGE_TX);
-                tma_load_2d(smem_u32(sRing + s * kStageBytes), &map_w, bar_full + 8 * s, kb * 64, g * H + nc * C::NT);
+                load_slice(&map_w, s, kb * 64, g * H + nc * C::NT);
               }
-          {                                                          // head: KB boxes of [head_pad x 64]
+          {                                                          // head: KB boxes of [head_pad x 64], dealt round-robin
             uint32_t s = acquire((uint32_t)(C::KB * P.head_pad * 128));
-            for (int kb = 0; kb < C::KB; ++kb)
-              tma_load_2d(smem_u32(sRing + s * kStageBytes + kb * P.head_pad * 128), &map_head, bar_full + 8 * s, kb * 64, 0);
+            for (int kb = (int)crank; kb < C::KB; kb += CS) {
+              uint32_t dst = smem_u32(sRing + s * kStageBytes + kb * P.head_pad * 128);
+              if (CS > 1) tma_load_2d_mc(dst, &map_head, bar_full + 8 * s, kb * 64, 0, kMask);
+              else tma_load_2d(dst, &map_head, bar_full + 8 * s, kb * 64, 0);
+            }
           }
         }
       }
@@ -248,7 +333,11 @@ sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
       uint32_t cnt = 0, gemm = 0;
       const uint32_t idesc = umma_idesc_bf16(C::NT), idesc_head = umma_idesc_bf16(P.head_pad);
       const uint32_t a_base = smem_u32(sA);
-      for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      auto release = [&](uint32_t s) {
+        if (CS > 1) umma_commit_mc(bar_empty + 8 * s, kMask);
+        else umma_commit(bar_empty + 8 * s);
+      };
+      for (int it = 0; it < P.iters; ++it) {
         for (int st = 0; st < n_steps; ++st) {
           // ---- input GEMM: K = 32 (two k-steps of the first K block)
           mbar_wait(bar_a, gemm & 1u, 2);
@@ -261,7 +350,7 @@ sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 2; ++j)
               umma_bf16(tmem_base + nc * C::NT, umma_desc_sw128(a_base + j * 32), umma_desc_sw128(b_base + j * 32), idesc, j > 0);
-            umma_commit(bar_empty + 8 * s);
+            release(s);
             ++cnt;
           }
           umma_commit(bar_acc);
@@ -280,7 +369,7 @@ sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
                 for (int j = 0; j < 4; ++j)
                   umma_bf16(tmem_base + nc * C::NT, umma_desc_sw128(a_base + kb * 16384 + j * 32),
                             umma_desc_sw128(b_base + j * 32), idesc, (kb | j) != 0);
-                umma_commit(bar_empty + 8 * s);
+                release(s);
                 ++cnt;
               }
             umma_commit(bar_acc);
@@ -299,7 +388,7 @@ sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
               for (int j = 0; j < 4; ++j)
                 umma_bf16(tmem_base, umma_desc_sw128(a_base + kb * 16384 + j * 32),
                           umma_desc_sw128(b_base + kb * P.head_pad * 128 + j * 32), idesc_head, (kb | j) != 0);
-            umma_commit(bar_empty + 8 * s);
+            release(s);
             ++cnt;
           }
           umma_commit(bar_acc);
@@ -307,8 +396,10 @@ sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
         }
       }
     }
+  }
   } else {
     // =============================== epilogue / compute warps ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int lq = warp & 3, cq = warp >> 2;
     const int m = lq * 32 + lane;                       // row of the tile == TMEM lane
     const int cbase = cq * C::CW;
@@ -318,10 +409,13 @@ sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     uint32_t acc_phase = 0;
     uint32_t xbits = 0;
 
-    for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+    for (int it = 0; it < P.iters; ++it) {
+      const int64_t tile_raw = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+      const bool tile_ok = tile_raw < P.n_tiles;                  // padding iterations compute but emit nothing
+      const int64_t tile = tile_ok ? tile_raw : 0;
       const int64_t bslot = tile / P.tiles_per_basis;
       const int64_t row_in_basis = (tile % P.tiles_per_basis) * 128 + m;
-      const bool valid = row_in_basis < P.spb;
+      const bool valid = tile_ok && row_in_basis < P.spb;
       const uint32_t basis = (uint32_t)P.basis_ids[bslot];
       const uint64_t shot = (uint64_t)(P.shot_offset + row_in_basis);
       const int64_t grow = bslot * P.spb + row_in_basis;         // global output row
@@ -492,6 +586,7 @@ sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();        // no CTA leaves while a peer may still multicast into it
   if (warp == 17) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
@@ -542,21 +637,70 @@ int sampler_tc_supported(const ddqst_dims* d) {
 
 int64_t sampler_tc_workspace_bytes(const ddqst_dims*, int64_t) { return 4096; }
 
-template <int H>
-static int launch_tc(const ddqst_dims* d, const char* pack, const PackLayout& pl, const TcParams& P0, cudaStream_t s) {
+template <int H, int CS>
+static int launch_tc_cs(const ddqst_dims* d, const char* pack, const PackLayout& pl, const TcParams& P0, cudaStream_t s) {
   using C = TcCfg<H>;
   TcParams P = P0;
   CUtensorMap map_w, map_dt, map_head;
-  DDQST_TRY(make_map(&map_w, pack + pl.w_bf16, (int64_t)d->num_blocks * 2 * H, H, C::NT));
-  DDQST_TRY(make_map(&map_dt, pack + pl.dt_bf16, H, 64, C::NT));
+  DDQST_TRY(make_map(&map_w, pack + pl.w_bf16, (int64_t)d->num_blocks * 2 * H, H, C::NT / CS));
+  DDQST_TRY(make_map(&map_dt, pack + pl.dt_bf16, H, 64, C::NT / CS));
   DDQST_TRY(make_map(&map_head, pack + pl.head_bf16, pl.head_pad, H, pl.head_pad));
   const int smem = tc_smem_bytes<H>(d->num_blocks);
-  DDQST_CUDA_OK(cudaFuncSetAttribute(sampler_tc_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  int grid = num_sms();
-  if ((int64_t)grid > P.n_tiles) grid = (int)P.n_tiles;
-  sampler_tc_kernel<H><<<grid, kThreads, smem, s>>>(map_w, map_dt, map_head, P);
-  DDQST_LAUNCH_OK();
+  auto kern = sampler_tc_kernel<H, CS>;
+  DDQST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  // persistent grid: as many CTAs as can be co-resident (one per SM, whole clusters), never more than the work
+  int max_ctas = num_sms() / CS * CS;
+  if (CS > 1) {
+    static int cached[8] = {0};
+    if (!cached[CS]) {
+      cfg.gridDim = dim3(max_ctas);
+      int nclusters = 0;
+      DDQST_CUDA_OK(cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg));
+      cached[CS] = nclusters > 0 ? nclusters : 1;
+    }
+    if (cached[CS] * CS < max_ctas) max_ctas = cached[CS] * CS;
+  }
+  int64_t want = (P.n_tiles + CS - 1) / CS * CS;
+  int grid = (int)(want < max_ctas ? want : max_ctas);
+  P.iters = (int32_t)((P.n_tiles + grid - 1) / grid);
+  cfg.gridDim = dim3(grid);
+  DDQST_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, map_w, map_dt, map_head, P));
   return DDQST_OK;
+}
+
+static int tc_cluster_size() {
+  static int cs = 0;
+  if (!cs) {
+    const char* e = getenv("DDQST_TC_CLUSTER");
+    cs = e ? atoi(e) : 2;
+    if (cs != 1 && cs != 2 && cs != 4) cs = 2;
+  }
+  return cs;
+}
+
+template <int H>
+static int launch_tc(const ddqst_dims* d, const char* pack, const PackLayout& pl, const TcParams& P, cudaStream_t s) {
+  switch (tc_cluster_size()) {
+    case 1: return launch_tc_cs<H, 1>(d, pack, pl, P, s);
+    case 4: return launch_tc_cs<H, 4>(d, pack, pl, P, s);
+    default: return launch_tc_cs<H, 2>(d, pack, pl, P, s);
+  }
+}
+
+#include "sampler_pair.cuh"
+
+static bool use_pair_kernel(int H) {
+  const char* e = getenv("DDQST_TC_KERNEL");
+  if (e && e[0] == 'v' && e[1] == '1') return false;
+  return H % 128 == 0;
 }
 
 static int dispatch_tc(const ddqst_dims* d, const char* pack, const PackLayout& pl, TcParams& P, cudaStream_t s) {
@@ -568,6 +712,13 @@ static int dispatch_tc(const ddqst_dims* d, const char* pack, const PackLayout& 
   P.tiles_per_basis = (P.spb + 127) / 128;
   P.n_tiles = P.tiles_per_basis * P.n_bases;
   if (P.n_tiles == 0) return DDQST_OK;
+  if (use_pair_kernel(d->hidden_dim)) {
+    switch (d->hidden_dim) {
+      case 128: return launch_pair<128>(d, pack, pl, P, s);
+      case 256: return launch_pair<256>(d, pack, pl, P, s);
+      default: return launch_pair<512>(d, pack, pl, P, s);
+    }
+  }
   switch (d->hidden_dim) {
     case 64: return launch_tc<64>(d, pack, pl, P, s);
     case 128: return launch_tc<128>(d, pack, pl, P, s);
@@ -684,11 +835,107 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap map_w, const float* __r
   }
 }
 
+
+// 2-CTA variant: C[256*mp, n] with one cta_group::2 MMA (M=256: 128 rows from each CTA of the pair, B split along N:
+// each CTA stages n/2 rows of W).  Exercises tcgen05.alloc/mma/commit .cta_group::2, the 2SM TMA form that
+// completes on the leader's barrier, and the cross-CTA "operand ready" arrive.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+umma2_selftest_kernel(const __grid_constant__ CUtensorMap map_w, const float* __restrict__ A, int n, int k,
+                      float* __restrict__ Cout) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + (k / 64) * 16384;                 // per K block: [n/2 rows x 128 B]
+  const int half = n / 2, KB = k / 64;
+  uint64_t* bars = (uint64_t*)(sB + KB * half * 128);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 4);
+  const uint32_t bar_full = smem_u32(bars), bar_acc = smem_u32(bars + 1), bar_a = smem_u32(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t crank = cluster_ctarank();
+  if (tid == 0) {
+    mbar_init(bar_full, 2); mbar_init(bar_acc, 1); mbar_init(bar_a, 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 17) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *((volatile uint32_t*)tmem_slot);
+  if (warp == 16 && lane == 0) {
+    if (crank == 0) mbar_expect_tx(bar_full, (uint32_t)(2 * KB * half * 128));
+    else mbar_arrive_leader(bar_full);
+    for (int kb = 0; kb < KB; ++kb)
+      tma_load_2d_2sm(smem_u32(sB + kb * half * 128), &map_w, bar_full, kb * 64, (int)crank * half);
+  }
+  if (tid < kEpiThreads) {
+    const int lq = warp & 3, cq = warp >> 2, m = lq * 32 + lane;
+    const float* arow = A + ((int64_t)blockIdx.x * 128 + m) * k;
+    for (int c0 = cq * 16; c0 < k; c0 += 64) {
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = pack_bf16(arow[c0 + 2 * i], arow[c0 + 2 * i + 1]);
+      const int kb = c0 >> 6, ch = (c0 & 63) >> 3;
+      *reinterpret_cast<uint4*>(sA + a_chunk_off(kb, m, ch)) = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(sA + a_chunk_off(kb, m, ch + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    fence_async_smem();
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    if (tid == 0) mbar_arrive_leader(bar_a);
+  }
+  if (warp == 17 && lane == 0 && crank == 0) {
+    mbar_wait_cluster(bar_a, 0, 30);
+    mbar_wait_cluster(bar_full, 0, 31);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16_m(256, n);
+    for (int kb = 0; kb < KB; ++kb)
+      for (int j = 0; j < 4; ++j)
+        umma2_bf16(tmem_base, umma_desc_sw128(smem_u32(sA) + kb * 16384 + j * 32),
+                   umma_desc_sw128(smem_u32(sB + kb * half * 128) + j * 32), idesc, (kb | j) != 0);
+    umma2_commit_mc(bar_acc, 3);
+  }
+  if (tid < kEpiThreads) {
+    const int lq = warp & 3, cq = warp >> 2, m = lq * 32 + lane;
+    mbar_wait(bar_acc, 0, 32);
+    tc_fence_after();
+    float* crow = Cout + ((int64_t)blockIdx.x * 128 + m) * n;
+    for (int c0 = cq * 16; c0 < n; c0 += 64) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + c0, r);
+      tmem_wait_ld16(r);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) crow[c0 + i] = __uint_as_float(r[i]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 17) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
 }  // namespace ddqst
 
 using namespace ddqst;
 
 extern "C" {
+
+int ddqst_selftest_umma2(const float* a, const uint16_t* w_bf16, int32_t m_pairs, int32_t n, int32_t k, float* c, void* stream) {
+  DDQST_TRY(check_arch());
+  DDQST_REQUIRE(m_pairs >= 1 && n >= 16 && n <= 256 && n % 16 == 0 && k >= 64 && k <= 512 && k % 64 == 0, DDQST_EINVAL_SHAPE, "selftest shape");
+  const int smem = 1024 + (k / 64) * 16384 + (k / 64) * (n / 2) * 128 + 256;
+  DDQST_REQUIRE(smem <= 232448, DDQST_EINVAL_SHAPE, "selftest needs %d bytes of shared memory", smem);
+  CUtensorMap map_w;
+  DDQST_TRY(make_map(&map_w, w_bf16, n, k, n / 2));
+  DDQST_CUDA_OK(cudaFuncSetAttribute(umma2_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma2_selftest_kernel<<<2 * m_pairs, kThreads, smem, (cudaStream_t)stream>>>(map_w, a, n, k, c);
+  DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
 
 int ddqst_selftest_umma(const float* a, const uint16_t* w_bf16, int32_t m_tiles, int32_t n, int32_t k, float* c, void* stream) {
   DDQST_TRY(check_arch());

@@ -184,6 +184,9 @@ int ddqst_selftest_philox(const uint32_t* ctr_key /* [n,6] */, int64_t n, uint32
 /* one tcgen05 GEMM C[M=128*mt, N] = A[M,K] bf16 . W[N,K]^T bf16 through the sampler's operand paths */
 int ddqst_selftest_umma(const float* a /* [M,K] fp32 */, const uint16_t* w_bf16 /* [N,K] */, int32_t m_tiles,
                         int32_t n, int32_t k, float* c /* [M,N] */, void* stream);
+/* the same through one cta_group::2 MMA: M = 256*m_pairs rows, n <= 256, CTA pair shares the B operand */
+int ddqst_selftest_umma2(const float* a, const uint16_t* w_bf16, int32_t m_pairs, int32_t n, int32_t k, float* c,
+                         void* stream);
 /* synchronises the device; returns the first pipeline-timeout code a tcgen05 kernel recorded (0 = none) */
 int ddqst_debug_tc_status(void);
 

@@ -343,3 +343,51 @@ def test_error_codes(dq):
         diff.sample([0], 10)
     diff32 = dq.DiscreteDiffusion(m, 10, "cuda", precision="fp32")
     assert diff32.p_sample(10, 0, 2).shape == (10, 2)
+
+
+# ------------------------------------------------------------------------------------------ CTA-pair pipelined sampler
+@pytest.mark.parametrize("H,L,N", [(128, 2, 4), (256, 3, 5), (512, 4, 8), (512, 2, 10)])
+def test_pair_kernel_teacher_forced_and_consistency(dq, H, L, N):
+    """hidden_dim % 128 == 0 selects the cta_group::2 chunk-pipelined kernel: logits within 1e-2 (relative to the
+    largest logit) of the fp32 oracle at every step, draws identical outside the guard band, histogram == bincount,
+    shot-split invariance, odd tile counts (padding tile in the pair) and several bases per launch."""
+    T, NB, E = 6, 3 ** min(N, 5), 32
+    torch.manual_seed(H + N)
+    m = dq.ConditionalD3PM(N, NB, T, E, H, L)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.03 * torch.randn_like(p))
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    seed, basis, shots, off = 77, NB - 1, 300, 5            # 300 shots -> 3 tiles: one pair + a padded pair
+    betas, Q = orc.cosine_schedule(T)
+    final, traj = orc.p_sample_posterior(sd, betas, Q, shots, basis, N, seed, shot_offset=off, trajectory=True)
+    diff = dq.DiscreteDiffusion(m, T, "cuda", seed=seed, precision="bf16")
+    total = bad = 0
+    for k, t in enumerate(range(T, 0, -1)):
+        x_prev, logits = diff.sample_step(traj[k].cuda(), basis, t, shot_offset=off)
+        want = orc.denoiser_forward(sd, traj[k], torch.full((shots,), t), torch.full((shots,), basis), N)
+        err = (logits.cpu() - want).abs().max().item()
+        assert err <= 1e-2 * want.abs().max().item() + 1e-3, (t, err, want.abs().max().item())
+        mism = x_prev.cpu() != traj[k + 1]
+        total += mism.numel()
+        bad += int(mism.sum())
+    assert bad / total <= 2e-2, (bad, total)
+    assert dq._lib.load().ddqst_debug_tc_status() == 0
+    bases = [0, basis, 1]
+    hist, packed = diff.sample(bases, 700, return_bits=True)
+    h = hist.view(torch.int32).cpu().numpy()
+    assert (h.sum(axis=1) == 700).all()
+    for i in range(3):
+        assert np.array_equal(h[i], np.bincount(packed[i].cpu().numpy().astype(np.int64), minlength=1 << N))
+    _, p1 = diff.sample(bases, 250, shot_offset=0, return_bits=True)
+    _, p2 = diff.sample(bases, 450, shot_offset=250, return_bits=True)
+    assert torch.equal(torch.cat([p1, p2], dim=1), packed)
+    assert dq._lib.load().ddqst_debug_tc_status() == 0
+    # distribution vs the fp32 exact path
+    exact = dq.DiscreteDiffusion(m, T, "cuda", seed=seed, precision="fp32")
+    n_big = 40_000
+    hb = diff.sample([basis], n_big)[0].view(torch.int32).cpu().numpy().astype(np.float64) / n_big
+    he = exact.sample([basis], n_big)[0].view(torch.int32).cpu().numpy().astype(np.float64) / n_big
+    tv = 0.5 * np.abs(hb - he).sum()
+    assert tv < 0.5 * np.sqrt((1 << N) / n_big) + 0.02, tv
