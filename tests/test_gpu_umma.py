@@ -25,7 +25,7 @@ def test_umma_gemm(mt, n, k):
     assert err < 2e-3 * np.sqrt(k), err
 
 
-@pytest.mark.parametrize("mp,n,k", [(1, 64, 64), (1, 256, 128), (2, 128, 512), (1, 16, 256), (1, 256, 512)])
+@pytest.mark.parametrize("mp,n,k", [(1, 64, 64), (1, 256, 128), (2, 128, 512), (1, 16, 256), (1, 256, 256)])
 def test_umma_gemm_cta_pair(mp, n, k):
     """cta_group::2: one MMA spans a CTA pair (M=256), each CTA stages half of W."""
     import ddqst_b200 as dq
