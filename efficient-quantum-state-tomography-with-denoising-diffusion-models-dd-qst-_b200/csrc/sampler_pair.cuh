@@ -93,17 +93,20 @@ sampler_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
   const uint32_t tmem_base = *((volatile uint32_t*)tmem_slot);
 
   if (warp >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 16) {
       // =============================== TMA producer (both CTAs: own half of every B tile) ===============================
-      if (lane == 0) {
-        tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_dt); tma_prefetch_desc(&map_head);
+      {
+        const uint32_t elected = elect_one();           // whole warp converged; one lane issues
+        if (elected) { tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_dt); tma_prefetch_desc(&map_head); }
         uint32_t cnt = 0;
         auto acquire = [&](uint32_t bytes_both) -> uint32_t {
           uint32_t s = cnt % kRing2, ph = (cnt / kRing2) & 1u;
           mbar_wait(bar_empty + 8 * s, ph ^ 1u, 1);
-          if (crank == 0) mbar_expect_tx(bar_full + 8 * s, bytes_both);
-          else mbar_arrive_leader(bar_full + 8 * s);
+          if (elected) {
+            if (crank == 0) mbar_expect_tx(bar_full + 8 * s, bytes_both);
+            else mbar_arrive_leader(bar_full + 8 * s);
+          }
           ++cnt;
           return s;
         };
@@ -111,38 +114,47 @@ sampler_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           for (int st = 0; st < n_steps; ++st) {
             for (int n = 0; n < NCH; ++n) {                                   // input table, K block 0 only
               uint32_t s = acquire(2 * 8192);
-              tma_load_2d_2sm(smem_u32(sRing + s * kStageBytes), &map_dt, bar_full + 8 * s, 0, n * 128 + (int)crank * 64);
+              if (elected) tma_load_2d_2sm(smem_u32(sRing + s * kStageBytes), &map_dt, bar_full + 8 * s, 0, n * 128 + (int)crank * 64);
             }
             for (int g = 0; g < 2 * L; ++g)
               for_each_item(NCH, [&](int n, int k, int, int) {
                 uint32_t s = acquire(2 * 16384);
                 uint32_t dst = smem_u32(sRing + s * kStageBytes);
                 int row = g * H + n * 128 + (int)crank * 64;
-                tma_load_2d_2sm(dst, &map_w, bar_full + 8 * s, (2 * k) * 64, row);
-                tma_load_2d_2sm(dst + 8192, &map_w, bar_full + 8 * s, (2 * k + 1) * 64, row);
+                if (elected) {
+                  tma_load_2d_2sm(dst, &map_w, bar_full + 8 * s, (2 * k) * 64, row);
+                  tma_load_2d_2sm(dst + 8192, &map_w, bar_full + 8 * s, (2 * k + 1) * 64, row);
+                }
               });
             for (int k = 0; k < NCH; ++k) {                                   // head, K chunk k
               uint32_t s = acquire((uint32_t)(2 * 2 * hp2 * 128));
               uint32_t dst = smem_u32(sRing + s * kStageBytes);
-              tma_load_2d_2sm(dst, &map_head, bar_full + 8 * s, (2 * k) * 64, (int)crank * hp2);
-              tma_load_2d_2sm(dst + hp2 * 128, &map_head, bar_full + 8 * s, (2 * k + 1) * 64, (int)crank * hp2);
+              if (elected) {
+                tma_load_2d_2sm(dst, &map_head, bar_full + 8 * s, (2 * k) * 64, (int)crank * hp2);
+                tma_load_2d_2sm(dst + hp2 * 128, &map_head, bar_full + 8 * s, (2 * k + 1) * 64, (int)crank * hp2);
+              }
             }
           }
         }
       }
     } else if (warp == 17 && crank == 0) {
       // =============================== MMA issuer (leader CTA only) ===============================
-      if (lane == 0) {
+      {
+        const uint32_t elected = elect_one();           // whole warp converged; one lane issues
         uint32_t cnt = 0, slot = 0;
         const uint32_t idesc = umma_idesc_bf16_m(256, 128), idesc_head = umma_idesc_bf16_m(256, P.head_pad);
-        const uint32_t a_base = smem_u32(sA);
+        const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
+        const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sRing));
         auto stage_wait = [&]() -> uint32_t {
           uint32_t s = cnt % kRing2, ph = (cnt / kRing2) & 1u;
           mbar_wait_cluster(bar_full + 8 * s, ph, 3);
           tc_fence_after();
           return s;
         };
-        auto stage_release = [&](uint32_t s) { umma2_commit_mc(bar_empty + 8 * s, 3); ++cnt; };
+        auto stage_release = [&](uint32_t s) {
+          if (elected) umma2_commit_mc(bar_empty + 8 * s, 3);
+          ++cnt;
+        };
         for (int it = 0; it < P.iters; ++it) {
           for (int st = 0; st < n_steps; ++st) {
             // ---- input GEMM (K = 32): needs only the input rows (published with ready[0])
@@ -150,28 +162,37 @@ sampler_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
             tc_fence_after();
             for (int n = 0; n < NCH; ++n) {
               uint32_t s = stage_wait();
-              uint32_t b_base = smem_u32(sRing + s * kStageBytes);
+              if (elected) {
+                const uint64_t bd = desc_adv(b_desc0, s * kStageBytes);
 #pragma unroll
-              for (int j = 0; j < 2; ++j)
-                umma2_bf16(tmem_base + n * 128, umma_desc_sw128(a_base + j * 32), umma_desc_sw128(b_base + j * 32), idesc, j > 0);
+                for (int j = 0; j < 2; ++j)
+                  umma2_bf16(tmem_base + n * 128, desc_adv(a_desc0, j * 32), desc_adv(bd, j * 32), idesc, j > 0);
+              }
               stage_release(s);
             }
-            for (int n = 0; n < NCH; ++n) umma2_commit_mc(bar_acc + 8 * n, 3);
+            if (elected)
+              for (int n = 0; n < NCH; ++n) umma2_commit_mc(bar_acc + 8 * n, 3);
+            __syncwarp();
             ++slot;
             // ---- hidden GEMMs, chunk pipelined
             for (int g = 0; g < 2 * L; ++g) {
               for_each_item(NCH, [&](int n, int k, int wait_c, int commit_n) {
                 if (wait_c >= 0) { mbar_wait_cluster(bar_ready + 8 * wait_c, slot & 1u, 4); tc_fence_after(); }
                 uint32_t s = stage_wait();
-                uint32_t b_base = smem_u32(sRing + s * kStageBytes);
+                if (elected) {
+                  const uint64_t ad = desc_adv(a_desc0, (uint32_t)k * 32768u);
+                  const uint64_t bd = desc_adv(b_desc0, s * kStageBytes);
+                  const uint32_t d_tmem = tmem_base + n * 128;
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                  for (int h = 0; h < 2; ++h)
 #pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    umma2_bf16(tmem_base + n * 128, umma_desc_sw128(a_base + (2 * k + h) * 16384 + j * 32),
-                               umma_desc_sw128(b_base + h * 8192 + j * 32), idesc, (k | h | j) != 0);
+                    for (int j = 0; j < 4; ++j)
+                      umma2_bf16(d_tmem, desc_adv(ad, h * 16384 + j * 32), desc_adv(bd, h * 8192 + j * 32), idesc,
+                                 (uint32_t)((k | h | j) != 0));
+                }
                 stage_release(s);
-                if (commit_n >= 0) umma2_commit_mc(bar_acc + 8 * commit_n, 3);
+                if (commit_n >= 0 && elected) umma2_commit_mc(bar_acc + 8 * commit_n, 3);
+                __syncwarp();
               });
               ++slot;
             }
@@ -180,16 +201,21 @@ sampler_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
               mbar_wait_cluster(bar_ready + 8 * k, slot & 1u, 6);
               tc_fence_after();
               uint32_t s = stage_wait();
-              uint32_t b_base = smem_u32(sRing + s * kStageBytes);
+              if (elected) {
+                const uint64_t ad = desc_adv(a_desc0, (uint32_t)k * 32768u);
+                const uint64_t bd = desc_adv(b_desc0, s * kStageBytes);
 #pragma unroll
-              for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  umma2_bf16(tmem_base, umma_desc_sw128(a_base + (2 * k + h) * 16384 + j * 32),
-                             umma_desc_sw128(b_base + h * hp2 * 128 + j * 32), idesc_head, (k | h | j) != 0);
+                  for (int j = 0; j < 4; ++j)
+                    umma2_bf16(tmem_base, desc_adv(ad, h * 16384 + j * 32), desc_adv(bd, h * hp2 * 128 + j * 32), idesc_head,
+                               (uint32_t)((k | h | j) != 0));
+              }
               stage_release(s);
             }
-            for (int n = 0; n < NCH; ++n) umma2_commit_mc(bar_acc + 8 * n, 3);
+            if (elected)
+              for (int n = 0; n < NCH; ++n) umma2_commit_mc(bar_acc + 8 * n, 3);
+            __syncwarp();
             ++slot;
           }
         }

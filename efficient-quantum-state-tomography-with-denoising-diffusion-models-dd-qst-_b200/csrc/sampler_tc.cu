@@ -183,6 +183,17 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16_m(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// one lane of a converged warp (elect.sync): the issuing warps stay converged so that descriptors and
+// addresses are warp-uniform; a single diverged lane makes ptxas emit R2UR/ELECT waterfall loops (~150 cycles
+// per tcgen05.mma, measured) and starves the tensor pipe.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+  return pred;
+}
+// advance a shared-memory descriptor by a byte offset (start-address field is in 16-byte units)
+__device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
 __device__ __forceinline__ float silu_fast(float v) {
   float h = 0.5f * v, th;
   asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
