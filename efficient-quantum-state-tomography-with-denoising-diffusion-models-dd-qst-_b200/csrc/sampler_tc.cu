@@ -343,13 +343,18 @@ sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
     }
   } else if (warp == 17) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    {
+      const uint32_t elected = elect_one();           // warp converged, one lane issues (see elect_one)
       uint32_t cnt = 0, gemm = 0;
       const uint32_t idesc = umma_idesc_bf16(C::NT), idesc_head = umma_idesc_bf16(P.head_pad);
-      const uint32_t a_base = smem_u32(sA);
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sRing));
       auto release = [&](uint32_t s) {
-        if (CS > 1) umma_commit_mc(bar_empty + 8 * s, kMask);
-        else umma_commit(bar_empty + 8 * s);
+        if (elected) {
+          if (CS > 1) umma_commit_mc(bar_empty + 8 * s, kMask);
+          else umma_commit(bar_empty + 8 * s);
+        }
+        __syncwarp();
       };
       for (int it = 0; it < P.iters; ++it) {
         for (int st = 0; st < n_steps; ++st) {
@@ -360,14 +365,17 @@ sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
             uint32_t s = cnt % kStages, ph = (cnt / kStages) & 1u;
             mbar_wait(bar_full + 8 * s, ph, 3);
             tc_fence_after();
-            uint32_t b_base = smem_u32(sRing + s * kStageBytes);
+            if (elected) {
+              const uint64_t bd = desc_adv(b_desc0, s * kStageBytes);
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              umma_bf16(tmem_base + nc * C::NT, umma_desc_sw128(a_base + j * 32), umma_desc_sw128(b_base + j * 32), idesc, j > 0);
+              for (int j = 0; j < 2; ++j)
+                umma_bf16(tmem_base + nc * C::NT, desc_adv(a_desc0, j * 32), desc_adv(bd, j * 32), idesc, j > 0);
+            }
             release(s);
             ++cnt;
           }
-          umma_commit(bar_acc);
+          if (elected) umma_commit(bar_acc);
+          __syncwarp();
           ++gemm;
           // ---- 2L hidden GEMMs
           for (int g = 0; g < 2 * L; ++g) {
@@ -378,15 +386,18 @@ sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
                 uint32_t s = cnt % kStages, ph = (cnt / kStages) & 1u;
                 mbar_wait(bar_full + 8 * s, ph, 5);
                 tc_fence_after();
-                uint32_t b_base = smem_u32(sRing + s * kStageBytes);
+                if (elected) {
+                  const uint64_t ad = desc_adv(a_desc0, (uint32_t)kb * 16384u);
+                  const uint64_t bd = desc_adv(b_desc0, s * kStageBytes);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  umma_bf16(tmem_base + nc * C::NT, umma_desc_sw128(a_base + kb * 16384 + j * 32),
-                            umma_desc_sw128(b_base + j * 32), idesc, (kb | j) != 0);
+                  for (int j = 0; j < 4; ++j)
+                    umma_bf16(tmem_base + nc * C::NT, desc_adv(ad, j * 32), desc_adv(bd, j * 32), idesc, (uint32_t)((kb | j) != 0));
+                }
                 release(s);
                 ++cnt;
               }
-            umma_commit(bar_acc);
+            if (elected) umma_commit(bar_acc);
+          __syncwarp();
             ++gemm;
           }
           // ---- head GEMM: N = head_pad
@@ -396,16 +407,19 @@ sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_consta
             uint32_t s = cnt % kStages, ph = (cnt / kStages) & 1u;
             mbar_wait(bar_full + 8 * s, ph, 7);
             tc_fence_after();
-            uint32_t b_base = smem_u32(sRing + s * kStageBytes);
-            for (int kb = 0; kb < C::KB; ++kb)
+            if (elected) {
+              const uint64_t bd = desc_adv(b_desc0, s * kStageBytes);
+              for (int kb = 0; kb < C::KB; ++kb)
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                umma_bf16(tmem_base, umma_desc_sw128(a_base + kb * 16384 + j * 32),
-                          umma_desc_sw128(b_base + kb * P.head_pad * 128 + j * 32), idesc_head, (kb | j) != 0);
+                for (int j = 0; j < 4; ++j)
+                  umma_bf16(tmem_base, desc_adv(a_desc0, kb * 16384 + j * 32), desc_adv(bd, kb * P.head_pad * 128 + j * 32),
+                            idesc_head, (uint32_t)((kb | j) != 0));
+            }
             release(s);
             ++cnt;
           }
-          umma_commit(bar_acc);
+          if (elected) umma_commit(bar_acc);
+          __syncwarp();
           ++gemm;
         }
       }
