@@ -493,6 +493,22 @@ def haar_state(num_qubits: int, seed: int = 0) -> np.ndarray:
     return v / np.linalg.norm(v)
 
 
+def born_probabilities_all(psi: np.ndarray, num_qubits: int) -> np.ndarray:
+    """Outcome distributions of a pure state in ALL 3^N Pauli bases (product order, letter 0 slowest) -> [3^N, 2^N].
+    Same physics as ``born_probabilities`` but expands one qubit at a time (3^N * 2^N * N work instead of 3^N * 4^N)."""
+    H = np.array([[1, 1], [1, -1]], dtype=complex) / math.sqrt(2)
+    Sdg = np.array([[1, 0], [0, -1j]], dtype=complex)
+    rots = [H, H @ Sdg, np.eye(2, dtype=complex)]
+    dim = 1 << num_qubits
+    states = np.asarray(psi, dtype=complex).reshape(1, dim)
+    for i in range(num_qubits):
+        lo = 1 << i
+        v = states.reshape(states.shape[0], dim // (2 * lo), 2, lo)
+        states = np.stack([np.einsum("ab,nhbl->nhal", r, v) for r in rots], axis=1).reshape(-1, dim)
+    p = np.abs(states) ** 2
+    return p / p.sum(axis=1, keepdims=True)
+
+
 def born_probabilities(psi_or_rho: np.ndarray, num_qubits: int, basis: str) -> np.ndarray:
     """Outcome distribution when qubit i is rotated by H (X) or H.Sdg (Y) before a Z measurement
     (RQC/build_dataset.py:94-96); outcome index bit i = qubit i."""
