@@ -248,7 +248,7 @@ int64_t ddqst_workspace_bytes(int op, const ddqst_dims* d, int64_t batch, int pr
     }
     case DDQST_OP_LINEAR_INVERSION: {
       // batch = n_slots ; W int32 [n_slots, 2^N]
-      return align_up(batch * ((int64_t)4 << d->num_qubits), 256) + 256;
+      { int64_t a = batch * ((int64_t)4 << d->num_qubits), b = (int64_t)8 << (2 * d->num_qubits); return align_up(a > b ? a : b, 256) + 256; }
     }
     case DDQST_OP_PSD:
     case DDQST_OP_METRICS: {

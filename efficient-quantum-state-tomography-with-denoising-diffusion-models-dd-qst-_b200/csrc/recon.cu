@@ -55,8 +55,138 @@ __global__ void __launch_bounds__(256) histogram_kernel(const T* __restrict__ da
   }
 }
 
+// N <= 8 fast path: every thread owns a private set of 256 16-bit counters in shared memory, laid out
+// [bin>>1][lane] so that a warp's 32 read-modify-writes always hit 32 different banks: no atomics and no
+// conflicts in the streaming loop (LDS.U16 / IADD / STS.U16 per shot).  Counters are folded into global
+// memory with one atomicAdd per (warp, bin) at the end (and before a private counter could overflow).
+template <typename T>
+__global__ void __launch_bounds__(128) histogram_private_kernel(const T* __restrict__ data, int64_t n, int nbins,
+                                                                uint32_t* __restrict__ hist) {
+  extern __shared__ __align__(16) uint8_t shp[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* wbase = shp + warp * 16384;                  // 128 word-rows x 32 lanes x 4 B
+  uint8_t* mine = wbase + lane * 4;
+  uint32_t* w32 = reinterpret_cast<uint32_t*>(wbase);
+  for (int i = lane; i < 4096; i += 32) w32[i] = 0;
+  __syncwarp();
+  constexpr int VEC = 16 / sizeof(T);
+  const int64_t nvec = n / VEC;
+  const uint4* v4 = reinterpret_cast<const uint4*>(data);
+  const uint32_t mask_bins = (uint32_t)nbins - 1u;
+  auto bump = [&](uint32_t bin) {
+    uint16_t* c = reinterpret_cast<uint16_t*>(mine + ((bin >> 1) << 7) + ((bin & 1u) << 1));
+    *c = (uint16_t)(*c + 1);
+  };
+  auto fold = [&]() {                                   // warp-cooperative: lane l sums bins l, l+32, .. over all lanes
+    __syncwarp();
+    for (int b0 = 0; b0 < nbins; b0 += 32) {
+      uint32_t bin = b0 + lane, sum = 0;
+      if ((int)bin < nbins) {
+        for (int it = 0; it < 32; ++it) {
+          int l2 = (lane + it) & 31;                    // rotate so the 32 readers hit 32 banks
+          sum += *reinterpret_cast<uint16_t*>(wbase + l2 * 4 + ((bin >> 1) << 7) + ((bin & 1u) << 1));
+        }
+        if (sum) atomicAdd(hist + bin, sum);
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < 4096; i += 32) w32[i] = 0;
+    __syncwarp();
+  };
+  int since_fold = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    uint4 w;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(v4 + i));
+    uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      uint32_t word = words[(k * sizeof(T)) / 4];
+      bump((word >> (8 * ((k * sizeof(T)) % 4))) & (sizeof(T) == 1 ? 0xFFu : 0xFFFFu) & mask_bins);
+    }
+    if (++since_fold == 65535 / VEC) {                  // a private counter cannot have exceeded 65535 yet
+      // warp-uniform trip counts are not guaranteed at the tail, so only fold when the whole warp is here
+      if (__activemask() == 0xFFFFFFFFu) { fold(); since_fold = 0; }
+    }
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) atomicAdd(hist + ((uint32_t)data[i] & mask_bins), 1u);
+  __syncwarp();
+  fold();
+}
+
 // ------------------------------------------------------------------------------------ linear inversion
-// pass 1: W[slot,:] = WHT(hist[slot,:]) (exact integers)
+// Canonical data (all 3^N bases in product order), N <= 10: one warp per basis.  The warp transforms the whole
+// histogram row in registers (shuffles for the low 5 index bits, register butterflies above) and keeps only the
+// 2^k coefficients whose mask contains every Y/Z position of the basis (k = number of X letters): exactly the
+// Pauli strings that the first-compatible-basis rule (RQC/reconstruct.py:32-38) assigns to this basis.  They are
+// written, already divided by the shot count, into a table indexed like rho's X-mask diagonals: Tc[xm][z].
+template <int E>
+__global__ void __launch_bounds__(256) coeff_table_kernel(const uint32_t* __restrict__ hist, const int64_t* __restrict__ shots,
+                                                          int n_slots, int N, int kron, double* __restrict__ Tc) {
+  const int b = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (b >= n_slots) return;
+  const int dim = 1 << N;
+  int v[E];
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    int s = j * 32 + lane;
+    v[j] = s < dim ? (int)hist[(int64_t)b * dim + s] : 0;
+  }
+  const int low = N < 5 ? N : 5;
+  for (int i = 0; i < low; ++i) {
+    const bool upper = (lane >> i) & 1;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      int other = __shfl_xor_sync(0xFFFFFFFFu, v[j], 1 << i);
+      v[j] = upper ? other - v[j] : v[j] + other;
+    }
+  }
+#pragma unroll
+  for (int bit = 1; bit < E; bit <<= 1) {
+#pragma unroll
+    for (int j = 0; j < E; ++j)
+      if (!(j & bit)) { int a = v[j], c = v[j | bit]; v[j] = a + c; v[j | bit] = a - c; }
+  }
+  uint32_t bx = 0, bz = 0;                               // label-space masks: X-or-Y letters, Y-or-Z letters
+  int rem = b;
+  for (int i = N - 1; i >= 0; --i) { int d = rem % 3; rem /= 3; if (d != 2) bx |= 1u << i; if (d != 0) bz |= 1u << i; }
+  const double sh = (double)shots[b];
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    uint32_t m = (uint32_t)(j * 32 + lane);
+    if ((int)m < dim && (m & bz) == bz) {
+      uint32_t xl = m & bx, zl = m & bz;
+      if (kron != DDQST_KRON_REVERSED) { xl = __brev(xl) >> (32 - N); zl = __brev(zl) >> (32 - N); }
+      Tc[(int64_t)xl * dim + zl] = sh > 0.0 ? (double)v[j] / sh : 0.0;
+    }
+  }
+}
+
+// rho[r, r^xm] = 2^-N * WHT_z(Tc[xm][z] * (-i)^{popc(xm&z)})[r], one CTA per X-mask
+__global__ void rho_from_table_kernel(const double* __restrict__ Tc, int N, double2* __restrict__ rho) {
+  extern __shared__ double2 g[];
+  const int dim = 1 << N;
+  const uint32_t xm = blockIdx.x;
+  for (int z = threadIdx.x; z < dim; z += blockDim.x) {
+    double coeff = (xm == 0 && z == 0) ? 1.0 : Tc[(int64_t)xm * dim + z];
+    int ny = __popc(xm & (uint32_t)z) & 3;
+    g[z] = make_double2(ny == 0 ? coeff : (ny == 2 ? -coeff : 0.0), ny == 1 ? -coeff : (ny == 3 ? coeff : 0.0));
+  }
+  __syncthreads();
+  for (int len = 1; len < dim; len <<= 1) {
+    for (int i = threadIdx.x; i < dim / 2; i += blockDim.x) {
+      int lo = ((i / len) * 2 * len) + (i % len), hi = lo + len;
+      double2 a = g[lo], b = g[hi];
+      g[lo] = make_double2(a.x + b.x, a.y + b.y);
+      g[hi] = make_double2(a.x - b.x, a.y - b.y);
+    }
+    __syncthreads();
+  }
+  const double inv = 1.0 / (double)dim;
+  for (int r = threadIdx.x; r < dim; r += blockDim.x) rho[(int64_t)r * dim + (r ^ xm)] = make_double2(g[r].x * inv, g[r].y * inv);
+}
+
+// General path (arbitrary slot table): W[slot,:] = WHT(hist[slot,:]) (exact integers)
 __global__ void wht_hist_kernel(const uint32_t* __restrict__ hist, int N, int32_t* __restrict__ W) {
   extern __shared__ int32_t shw[];
   const int dim = 1 << N;
@@ -415,6 +545,20 @@ int ddqst_histogram(const void* packed, int elem_bytes, int64_t n, int32_t num_q
   DDQST_REQUIRE(((uintptr_t)packed & 15) == 0, DDQST_EINVAL_SHAPE, "packed bitstrings must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   const int nbins = 1 << num_qubits;
+  if (num_qubits <= 8) {                                 // private 16-bit counters, no atomics in the streaming loop
+    const int64_t nv = n / (16 / elem_bytes);
+    int64_t want_p = (nv + 127) / 128;
+    int grid_p = (int)(want_p < 1 ? 1 : (want_p > (int64_t)num_sms() * 3 ? (int64_t)num_sms() * 3 : want_p));
+    if (elem_bytes == 1) {
+      DDQST_CUDA_OK(cudaFuncSetAttribute(histogram_private_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+      histogram_private_kernel<uint8_t><<<grid_p, 128, 65536, s>>>((const uint8_t*)packed, n, nbins, hist);
+    } else {
+      DDQST_CUDA_OK(cudaFuncSetAttribute(histogram_private_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+      histogram_private_kernel<uint16_t><<<grid_p, 128, 65536, s>>>((const uint16_t*)packed, n, nbins, hist);
+    }
+    DDQST_LAUNCH_OK();
+    return DDQST_OK;
+  }
   const int use_smem = nbins * 4 <= 64 * 1024;
   const size_t smem = use_smem ? (size_t)nbins * 4 : 0;
   int64_t nvec = n / (16 / elem_bytes);
@@ -444,11 +588,30 @@ int ddqst_linear_inversion(const uint32_t* hist, const int64_t* shots, int32_t n
     DDQST_REQUIRE(n_slots == full, DDQST_EINVAL_SHAPE, "sel == NULL needs all 3^N = %lld bases in product order, got %d", (long long)full, n_slots);
   }
   const int dim = 1 << num_qubits;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int threads = dim / 2 < 32 ? 32 : (dim / 2 > 512 ? 512 : dim / 2);
+  if (!sel && num_qubits <= 10) {
+    // canonical data: per-basis warp WHT -> coefficient table Tc[4^N] -> per-X-mask WHT -> rho
+    const int64_t need_t = (int64_t)8 * dim * dim;
+    DDQST_REQUIRE(workspace && ws_bytes >= need_t, DDQST_EWORKSPACE, "linear inversion needs %lld workspace bytes, got %lld", (long long)need_t, (long long)ws_bytes);
+    double* Tc = (double*)workspace;
+    const int blocks = (int)(((int64_t)n_slots * 32 + 255) / 256);
+    switch (dim <= 32 ? 1 : dim / 32) {
+      case 1: coeff_table_kernel<1><<<blocks, 256, 0, s>>>(hist, shots, n_slots, num_qubits, kron, Tc); break;
+      case 2: coeff_table_kernel<2><<<blocks, 256, 0, s>>>(hist, shots, n_slots, num_qubits, kron, Tc); break;
+      case 4: coeff_table_kernel<4><<<blocks, 256, 0, s>>>(hist, shots, n_slots, num_qubits, kron, Tc); break;
+      case 8: coeff_table_kernel<8><<<blocks, 256, 0, s>>>(hist, shots, n_slots, num_qubits, kron, Tc); break;
+      case 16: coeff_table_kernel<16><<<blocks, 256, 0, s>>>(hist, shots, n_slots, num_qubits, kron, Tc); break;
+      default: coeff_table_kernel<32><<<blocks, 256, 0, s>>>(hist, shots, n_slots, num_qubits, kron, Tc); break;
+    }
+    DDQST_LAUNCH_OK();
+    rho_from_table_kernel<<<dim, threads, (size_t)dim * 16, s>>>(Tc, num_qubits, (double2*)rho);
+    DDQST_LAUNCH_OK();
+    return DDQST_OK;
+  }
   const int64_t need = (int64_t)n_slots * dim * 4;
   DDQST_REQUIRE(ws_bytes >= need && (workspace || need == 0), DDQST_EWORKSPACE, "linear inversion needs %lld workspace bytes, got %lld", (long long)need, (long long)ws_bytes);
-  cudaStream_t s = (cudaStream_t)stream;
   int32_t* W = (int32_t*)workspace;
-  const int threads = dim / 2 < 32 ? 32 : (dim / 2 > 512 ? 512 : dim / 2);
   if (n_slots > 0) {
     wht_hist_kernel<<<n_slots, threads, (size_t)dim * 4, s>>>(hist, num_qubits, W);
     DDQST_LAUNCH_OK();

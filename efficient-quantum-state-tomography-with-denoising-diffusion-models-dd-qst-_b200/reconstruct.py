@@ -151,7 +151,7 @@ def linear_inversion_raw(synthetic_data, num_qubits: int, convention: str = "rev
     dim = 1 << num_qubits
     rho = torch.empty(dim, dim, dtype=torch.complex128, device=dev)
     n_slots = hist.shape[0]
-    ws = _lib.workspace.get(n_slots * dim * 4 + 256, dev)
+    ws = _lib.workspace.get(max(n_slots * dim * 4, 8 * dim * dim) + 256, dev)
     kron = _lib.KRON_REVERSED if convention == "reversed" else _lib.KRON_UNREVERSED
     _lib.check(lib.ddqst_linear_inversion(_lib.ptr(hist) if n_slots else None, _lib.ptr(shots) if n_slots else None, n_slots,
                                           num_qubits, _lib.ptr(sel), kron, _lib.ptr(rho), _lib.ptr(ws), ws.numel(),
