@@ -10,6 +10,7 @@ from ._build import build
 from .diffusion import DiscreteDiffusion, NativeAdam, cosine_schedule, linear_schedule
 from .distributed import all_reduce_histograms, sample_sharded, shard_range
 from .model import ConditionalD3PM, pack_bits, unpack_bits
+from .notebook import BitstringDDM, SimpleMLP, UpgradedMLP
 from .reconstruct import (DensityMatrix, Statevector, basis_strings, get_coefficient, get_metrics, get_pauli_matrix,
                           histogram_samples, linear_inversion, linear_inversion_raw, make_positive_semidefinite,
                           state_fidelity)

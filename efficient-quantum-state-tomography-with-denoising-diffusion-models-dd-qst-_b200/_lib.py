@@ -23,8 +23,13 @@ class Dims(C.Structure):
                                          "num_blocks", "variant")]
 
 
+class Mlpdims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("num_bases", "num_timesteps", "embed_dim", "hidden_dim", "num_hidden")]
+
+
 _P, _I32, _I64, _U64, _U32, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_uint32, C.c_float
 _DP = C.POINTER(Dims)
+_MP = C.POINTER(Mlpdims)
 
 # name -> (restype, argtypes); mirrors include/ddqst.h one to one
 SIGNATURES = {
@@ -51,6 +56,11 @@ SIGNATURES = {
     "ddqst_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _F, C.c_int, _F, _P]),
     "ddqst_workspace_bytes": (_I64, [C.c_int, _DP, _I64, C.c_int]),
     "ddqst_sample_host": (C.c_int, [_DP, _P, _P, C.c_int, C.c_int, _P, _I32, _I64, _I64, _U64, _P, _P, _P, _I64, _P]),
+    "ddqst_mlp_param_count": (_I64, [_MP, _P]),
+    "ddqst_mlp_workspace_bytes": (_I64, [_MP, _I64]),
+    "ddqst_mlp_forward_saved": (C.c_int, [_MP, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
+    "ddqst_mlp_backward_saved": (C.c_int, [_MP, _P, _P, _P, _I64, _P, _P, _P, _I64, _P]),
+    "ddqst_mlp_sample": (C.c_int, [_MP, _P, _P, _I32, _I64, _I64, _U64, _P, _P, _P, _I64, _P]),
     "ddqst_selftest_philox": (C.c_int, [_P, _I64, _P, _P]),
     "ddqst_selftest_umma": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
     "ddqst_selftest_umma2": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),

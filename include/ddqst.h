@@ -167,6 +167,26 @@ int ddqst_adam_step(float* params, const float* grads, float* exp_avg, float* ex
                     int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
                     int decoupled, float grad_scale, void* stream);
 
+/* ---- M5 + the notebook DDM (single-qubit phase, config C1): SimpleMLP (NB c6:65-102: embed 32, hidden 128,
+ * num_hidden 2) and UpgradedMLP (NB c12:58-94: embed 128, hidden 256, num_hidden 3): cat[x, t_emb, b_emb] -> Linear/ReLU
+ * stack -> logits[B,2].  Flat parameters in state_dict order: time_emb.weight, basis_emb.weight, then
+ * net.{0,2,..}.{weight,bias}; offsets_out [2 + 2*(num_hidden+1)].  x is one bit per sample (bit 0 of a uint16).
+ * forward_saved / backward_saved serve autograd for BitstringDDM.train_step (NB c6:170-187, loss = CE(logits, x_0));
+ * mlp_sample is BitstringDDM.sample (NB c6:189-221): sched = [T+1 unused floats][Q[T+1,2,2]] with the notebook's
+ * p_stay schedule; output one uint8 per shot and/or counts[2]. */
+typedef struct { int32_t num_bases, num_timesteps, embed_dim, hidden_dim, num_hidden; } ddqst_mlp_dims;
+int64_t ddqst_mlp_param_count(const ddqst_mlp_dims* d, int64_t* offsets_out);
+int64_t ddqst_mlp_workspace_bytes(const ddqst_mlp_dims* d, int64_t batch);
+int ddqst_mlp_forward_saved(const ddqst_mlp_dims* d, const float* params, const uint16_t* x, const int32_t* t,
+                            const int32_t* basis, int64_t batch, float* logits_out, void* workspace, int64_t ws_bytes,
+                            void* stream);
+int ddqst_mlp_backward_saved(const ddqst_mlp_dims* d, const float* params, const int32_t* t, const int32_t* basis,
+                             int64_t batch, const float* dlogits, float* grads, void* workspace, int64_t ws_bytes,
+                             void* stream);
+int ddqst_mlp_sample(const ddqst_mlp_dims* d, const float* params, const float* sched, int32_t basis_id, int64_t n,
+                     int64_t shot_offset, uint64_t seed, uint8_t* out_bits, uint32_t* out_hist, void* workspace,
+                     int64_t ws_bytes, void* stream);
+
 /* ---- workspace sizes */
 enum { DDQST_OP_FORWARD = 0, DDQST_OP_SAMPLE = 1, DDQST_OP_LINEAR_INVERSION = 2, DDQST_OP_PSD = 3,
        DDQST_OP_FIDELITY_MIXED = 4, DDQST_OP_TRAIN = 5, DDQST_OP_METRICS = 6 };
