@@ -50,8 +50,9 @@ sampler_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
                     const __grid_constant__ CUtensorMap map_head, const TcParams P) {
   using C = PairCfg<H>;
   constexpr int NCH = C::NCH;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;   // no static shared memory in this kernel: the dynamic window starts 1024-aligned (checked below)
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0) atomicCAS(&g_tc_abort, 0, 99);
   uint8_t* sA = smem;
   uint8_t* sRing = sA + C::A_BYTES;
   float* sG1 = (float*)(sRing + kRing2 * kStageBytes);
@@ -84,7 +85,7 @@ sampler_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   if (tid < kEpiThreads) {
-    for (int i = tid; i < L * H; i += kEpiThreads) { sB1[i] = P.bias1[i]; sB2[i] = P.bias2[i]; }
+    for (int i = tid; i < L * H; i += kEpiThreads) { sB1[i] = 0.5f * P.bias1[i]; sB2[i] = 0.5f * P.bias2[i]; }   // half biases, see E1
   }
   tc_fence_before();
   __syncthreads();
@@ -302,75 +303,81 @@ sampler_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           }
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         }
-        // ---- input epilogue
+        // ---- input epilogue: h0 -> residual registers, a = film_0(h0)
 #pragma unroll
         for (int n = 0; n < NCH; ++n) {
           wait_acc(n, 8);
+          const int c0 = n * 128 + cs * 32;
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
             uint32_t r[16];
-            const int c0 = n * 128 + cs * 32 + b * 16;
-            tmem_ld16(t_lane + c0, r);
+            tmem_ld16(t_lane + c0 + b * 16, r);
             tmem_wait_ld16(r);
             uint32_t o[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
+              const int c = c0 + b * 16 + 2 * i;
               float v0 = __uint_as_float(r[2 * i]), v1 = __uint_as_float(r[2 * i + 1]);
               xr[n][b * 8 + i] = pack_bf16(v0, v1);
-              o[i] = pack_bf16(fmaf(v0, sG1[c0 + 2 * i], sBeta[c0 + 2 * i]), fmaf(v1, sG1[c0 + 2 * i + 1], sBeta[c0 + 2 * i + 1]));
+              o[i] = pack_bf16(fmaf(v0, sG1[c], sBeta[c]), fmaf(v1, sG1[c + 1], sBeta[c + 1]));
             }
-            store16(c0, o);
+            store16(c0 + b * 16, o);
           }
           signal_ready(n);
         }
         ++slot;
 
         for (int l = 0; l < L; ++l) {
-          const float* b1 = sB1 + l * H;
+          // ---- E1: u = silu(acc + b1); sB1/sB2 hold HALF the biases: silu(z) = h + h*tanh(h) with h = z/2 = fma(acc, .5, b/2)
+          const float* hb1 = sB1 + l * H;
 #pragma unroll
           for (int n = 0; n < NCH; ++n) {
             wait_acc(n, 9);
+            const int c0 = n * 128 + cs * 32;
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
               uint32_t r[16];
-              const int c0 = n * 128 + cs * 32 + b * 16;
-              tmem_ld16(t_lane + c0, r);
+              tmem_ld16(t_lane + c0 + b * 16, r);
               tmem_wait_ld16(r);
               uint32_t o[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                o[i] = pack_bf16(silu_fast(__uint_as_float(r[2 * i]) + b1[c0 + 2 * i]),
-                                 silu_fast(__uint_as_float(r[2 * i + 1]) + b1[c0 + 2 * i + 1]));
-              store16(c0, o);
+              for (int i = 0; i < 8; ++i) {
+                const int c = c0 + b * 16 + 2 * i;
+                o[i] = pack_bf16(silu_half(fmaf(__uint_as_float(r[2 * i]), 0.5f, hb1[c])),
+                                 silu_half(fmaf(__uint_as_float(r[2 * i + 1]), 0.5f, hb1[c + 1])));
+              }
+              store16(c0 + b * 16, o);
             }
             signal_ready(n);
           }
           ++slot;
 
-          const float* b2 = sB2 + l * H;
+          // ---- E2: h = silu(h + acc + b2); a = film_{l+1}(h) (or h itself before the head)
+          const float* hb2 = sB2 + l * H;
           const bool last = (l == L - 1);
           const float* g1 = sG1 + (last ? 0 : (l + 1) * H);
           const float* be = sBeta + (last ? 0 : (l + 1) * H);
 #pragma unroll
           for (int n = 0; n < NCH; ++n) {
             wait_acc(n, 10);
+            const int c0 = n * 128 + cs * 32;
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
               uint32_t r[16];
-              const int c0 = n * 128 + cs * 32 + b * 16;
-              tmem_ld16(t_lane + c0, r);
+              tmem_ld16(t_lane + c0 + b * 16, r);
               tmem_wait_ld16(r);
               uint32_t o[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                uint32_t xo = xr[n][b * 8 + i];
-                float v0 = silu_fast(__uint_as_float(r[2 * i]) + b2[c0 + 2 * i] + bf16_lo(xo));
-                float v1 = silu_fast(__uint_as_float(r[2 * i + 1]) + b2[c0 + 2 * i + 1] + bf16_hi(xo));
-                uint32_t xn = pack_bf16(v0, v1);
+                const int c = c0 + b * 16 + 2 * i;
+                const uint32_t xo = xr[n][b * 8 + i];
+                float v0 = silu_half(fmaf(bf16_lo(xo), 0.5f, fmaf(__uint_as_float(r[2 * i]), 0.5f, hb2[c])));
+                float v1 = silu_half(fmaf(bf16_hi(xo), 0.5f, fmaf(__uint_as_float(r[2 * i + 1]), 0.5f, hb2[c + 1])));
+                const uint32_t xn = pack_bf16(v0, v1);
                 xr[n][b * 8 + i] = xn;
-                o[i] = last ? xn : pack_bf16(fmaf(v0, g1[c0 + 2 * i], be[c0 + 2 * i]), fmaf(v1, g1[c0 + 2 * i + 1], be[c0 + 2 * i + 1]));
+                o[i] = last ? xn : pack_bf16(fmaf(v0, g1[c], be[c]), fmaf(v1, g1[c + 1], be[c + 1]));
               }
-              store16(c0, o);
+              store16(c0 + b * 16, o);
             }
             signal_ready(n);
           }

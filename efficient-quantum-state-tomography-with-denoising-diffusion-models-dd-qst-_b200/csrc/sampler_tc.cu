@@ -123,6 +123,26 @@ __device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
                : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
 // UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -199,6 +219,12 @@ __device__ __forceinline__ float silu_fast(float v) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
   return fmaf(h, th, h);
 }
+// silu(2h) given h: h + h*tanh(h)
+__device__ __forceinline__ float silu_half(float h) {
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+  return fmaf(h, th, h);
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -257,8 +283,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 sampler_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_dt,
                   const __grid_constant__ CUtensorMap map_head, const TcParams P) {
   using C = TcCfg<H>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;   // no static shared memory in this kernel: the dynamic window starts 1024-aligned (checked below)
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0) atomicCAS(&g_tc_abort, 0, 99);
   uint8_t* sA = smem;
   uint8_t* sRing = sA + C::A_BYTES;
   float* sG1 = (float*)(sRing + kStages * kStageBytes);   // [L][H] 1+gamma
@@ -790,8 +817,9 @@ int sampler_tc_forward(const ddqst_dims*, const char*, const PackLayout&, const 
 __global__ void __launch_bounds__(kThreads, 1)
 umma_selftest_kernel(const __grid_constant__ CUtensorMap map_w, const float* __restrict__ A, int n, int k,
                      float* __restrict__ Cout) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;   // no static shared memory in this kernel: the dynamic window starts 1024-aligned (checked below)
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0) atomicCAS(&g_tc_abort, 0, 99);
   uint8_t* sA = smem;                        // k/64 blocks of 16 KB
   uint8_t* sB = sA + (k / 64) * 16384;       // one 64-row x 64-col tile (8 KB) per (nc, kb), all resident
   uint64_t* bars = (uint64_t*)(sB + (n / 64) * (k / 64) * 8192);
@@ -870,8 +898,9 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap map_w, const float* __r
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 umma2_selftest_kernel(const __grid_constant__ CUtensorMap map_w, const float* __restrict__ A, int n, int k,
                       float* __restrict__ Cout) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;   // no static shared memory in this kernel: the dynamic window starts 1024-aligned (checked below)
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0) atomicCAS(&g_tc_abort, 0, 99);
   uint8_t* sA = smem;
   uint8_t* sB = sA + (k / 64) * 16384;                 // per K block: [n/2 rows x 128 B]
   const int half = n / 2, KB = k / 64;
