@@ -7,7 +7,7 @@ plus the batched ``DiscreteDiffusion.sample(bases, n_shots)``, ``train_step`` an
 """
 from . import _lib
 from ._build import build
-from .diffusion import DiscreteDiffusion, NativeAdam, cosine_schedule, linear_schedule
+from .diffusion import DiscreteDiffusion, NativeAdam, TrainGraph, cosine_schedule, linear_schedule
 from .distributed import all_reduce_histograms, sample_sharded, shard_range
 from .model import ConditionalD3PM, pack_bits, unpack_bits
 from .notebook import BitstringDDM, SimpleMLP, UpgradedMLP
@@ -16,7 +16,7 @@ from .reconstruct import (DensityMatrix, Statevector, basis_strings, get_coeffic
                           state_fidelity)
 
 __all__ = [
-    "ConditionalD3PM", "DiscreteDiffusion", "NativeAdam", "cosine_schedule", "linear_schedule", "pack_bits", "unpack_bits",
+    "ConditionalD3PM", "DiscreteDiffusion", "NativeAdam", "TrainGraph", "cosine_schedule", "linear_schedule", "pack_bits", "unpack_bits",
     "DensityMatrix", "Statevector", "basis_strings", "get_coefficient", "get_metrics", "get_pauli_matrix",
     "histogram_samples", "linear_inversion", "linear_inversion_raw", "make_positive_semidefinite", "state_fidelity",
     "all_reduce_histograms", "sample_sharded", "shard_range", "build",

@@ -42,6 +42,7 @@ SIGNATURES = {
     "ddqst_sample": (C.c_int, [_DP, _P, _P, C.c_int, C.c_int, _P, _I32, _I64, _I64, _U64, _P, _P, _P, _I64, _P]),
     "ddqst_sample_step": (C.c_int, [_DP, _P, _P, C.c_int, C.c_int, _I32, _I32, _I64, _I64, _U64, _P, _P, _P, _P, _I64, _P]),
     "ddqst_q_sample": (C.c_int, [_P, _I32, _I32, C.c_int, _P, _P, _I64, _I64, _U64, _U32, _P, _P, _P]),
+    "ddqst_q_sample_dev": (C.c_int, [_P, _I32, _I32, C.c_int, _P, _P, _I64, _I64, _U64, _P, _P, _P, _P]),
     "ddqst_histogram": (C.c_int, [_P, C.c_int, _I64, _I32, _P, _P]),
     "ddqst_pack_bits": (C.c_int, [_P, _I64, _I32, _P, _P]),
     "ddqst_unpack_bits": (C.c_int, [_P, C.c_int, _I64, _I32, _P, _P]),
@@ -54,6 +55,10 @@ SIGNATURES = {
     "ddqst_forward_saved": (C.c_int, [_DP, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
     "ddqst_backward_saved": (C.c_int, [_DP, _P, _P, _P, _P, _I64, _P, _P, _P, _I64, _P]),
     "ddqst_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _F, C.c_int, _F, _P]),
+    "ddqst_cast_bf16": (C.c_int, [_P, _P, _I64, _P]),
+    "ddqst_train_forward_backward_tc": (C.c_int, [_DP, _P, _P, _P, _P, _P, _P, _I64, _F, _P, _P, _P, _I64, _P]),
+    "ddqst_adam_step_dev": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, C.c_int, _F, _P]),
+    "ddqst_selftest_gemm_tc": (C.c_int, [_P, _P, C.c_int, C.c_int, _I32, _I32, _I32, _I32, _P, _P]),
     "ddqst_workspace_bytes": (_I64, [C.c_int, _DP, _I64, C.c_int]),
     "ddqst_sample_host": (C.c_int, [_DP, _P, _P, C.c_int, C.c_int, _P, _I32, _I64, _I64, _U64, _P, _P, _P, _I64, _P]),
     "ddqst_mlp_param_count": (_I64, [_MP, _P]),

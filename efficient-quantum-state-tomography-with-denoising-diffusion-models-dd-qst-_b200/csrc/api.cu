@@ -260,7 +260,7 @@ int64_t ddqst_workspace_bytes(int op, const ddqst_dims* d, int64_t batch, int pr
       return 6 * 16 * dim * dim + 128 * dim + 8192;
     }
     case DDQST_OP_TRAIN:
-      return train_workspace_bytes(d, batch);
+      return precision == DDQST_PRECISION_BF16 ? train_tc_workspace_bytes(d, batch) : train_workspace_bytes(d, batch);
     default:
       set_error("unknown op %d", op);
       return -1;
@@ -394,10 +394,12 @@ int ddqst_sample_step(const ddqst_dims* d, const void* pack, const float* sched,
 namespace ddqst {
 __global__ void q_sample_kernel(const float* __restrict__ Q, int T, int N, int cumulative,
                                 const uint16_t* __restrict__ x0, const int32_t* __restrict__ t_in, int64_t batch,
-                                int64_t row_offset, uint64_t seed, uint32_t stream_id, uint16_t* __restrict__ xt,
+                                int64_t row_offset, uint64_t seed, uint32_t stream_id,
+                                const int64_t* __restrict__ stream_dev, uint16_t* __restrict__ xt,
                                 int32_t* __restrict__ t_out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch) return;
+  if (stream_dev) stream_id = (uint32_t)stream_dev[0];     // step counter kept on the device (CUDA-graph replay)
   uint64_t row = (uint64_t)(row_offset + i);
   int t;
   if (t_in) t = t_in[i];
@@ -448,7 +450,20 @@ int ddqst_q_sample(const float* Q, int32_t num_timesteps, int32_t num_qubits, in
   if (batch == 0) return DDQST_OK;
   DDQST_REQUIRE(Q && x0_packed && xt_packed, DDQST_EINVAL_SHAPE, "NULL argument");
   q_sample_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      Q, num_timesteps, num_qubits, cumulative, x0_packed, t, batch, row_offset, seed, stream_id, xt_packed, t_out);
+      Q, num_timesteps, num_qubits, cumulative, x0_packed, t, batch, row_offset, seed, stream_id, nullptr, xt_packed, t_out);
+  DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
+
+int ddqst_q_sample_dev(const float* Q, int32_t num_timesteps, int32_t num_qubits, int cumulative,
+                       const uint16_t* x0_packed, const int32_t* t, int64_t batch, int64_t row_offset, uint64_t seed,
+                       const int64_t* stream_id_dev, uint16_t* xt_packed, int32_t* t_out, void* stream) {
+  DDQST_TRY(check_arch());
+  DDQST_REQUIRE(num_qubits >= 1 && num_qubits <= 16 && num_timesteps >= 1 && batch >= 0, DDQST_EINVAL_SHAPE, "bad shape");
+  if (batch == 0) return DDQST_OK;
+  DDQST_REQUIRE(Q && x0_packed && xt_packed && stream_id_dev, DDQST_EINVAL_SHAPE, "NULL argument");
+  q_sample_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      Q, num_timesteps, num_qubits, cumulative, x0_packed, t, batch, row_offset, seed, 0u, stream_id_dev, xt_packed, t_out);
   DDQST_LAUNCH_OK();
   return DDQST_OK;
 }

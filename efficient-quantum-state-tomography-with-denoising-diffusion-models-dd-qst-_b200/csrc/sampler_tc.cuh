@@ -20,8 +20,10 @@ int sampler_tc_forward(const ddqst_dims* d, const char* pack, const PackLayout& 
                        const int32_t* t, const int32_t* basis, int64_t batch, float* logits, void* workspace,
                        int64_t ws_bytes, cudaStream_t s);
 
-// training step (train.cu)
+// training step (train.cu: fp32 CUDA cores; train_tc.cu: bf16 tcgen05)
 int64_t train_workspace_bytes(const ddqst_dims* d, int64_t batch);
+int64_t train_tc_workspace_bytes(const ddqst_dims* d, int64_t batch);
+int train_tc_abort_fetch();
 
 // shared by the fp32 reverse-step kernel and the tcgen05 epilogue so both draw identically
 // logit(q, c) supplies logits[q][c]; returns the packed x_{t-1}

@@ -1,0 +1,748 @@
+// Tensor-core training step (T1, RQC/main.py:105-115) for sm_100a: every GEMM of the denoiser's forward,
+// data-gradient and weight-gradient passes runs on tcgen05 (bf16 x bf16 -> fp32 accumulators in TMEM), fed by
+// 3-D TMA tensor maps, with the elementwise work of the reference's autograd graph fused into the epilogues:
+//
+//   forward   gb_l   = cond . Wfilm_l^T + b            (one launch, z = block)            RQC/model.py:9-10
+//             h_0    = xin . Win^T + b ; a_0 = h_0 (1+g_0) + beta_0                        RQC/model.py:53-56,11
+//             z1_l   = a_l . W1_l^T + b1 ; u_l = silu(z1_l)                                RQC/model.py:17-19
+//             z2_l   = h_l + u_l . W2_l^T + b2 ; h_{l+1} = silu(z2_l) ; a_{l+1} = FiLM     RQC/model.py:24,11
+//             logits = h_L . Whead^T + b ; mean CE ; dlogits                              RQC/model.py:70, RQC/main.py:110
+//   backward  dgrads with the stored weights read as MN-major operands (no transposed copies),
+//             wgrads with BOTH operands MN-major (dY^T . X, reduction over the batch), z-batched over layers,
+//             embedding gradients scattered from the epilogue, bias gradients by a deterministic column sum.
+//
+// Operands are bf16 (a bf16 shadow of the flat fp32 parameter buffer is kept current by the fused Adam kernel);
+// accumulation, the saved pre-activations z1/z2, the FiLM vectors and the residual stream stay fp32.
+//
+// GEMM kernel: one 128 x BN output tile per CTA, BK = 64, 4-stage TMA ring, warp 4 = TMA producer, warp 5 = MMA
+// issuer + TMEM allocator, warps 0-3 = epilogue (thread = output row, tcgen05.ld 32x32b).
+#include <cuda.h>
+
+#include "sampler_tc.cuh"
+#include "simt.cuh"
+#include "tc_ptx.cuh"
+
+namespace ddqst {
+
+constexpr int kGtThreads = 192;
+constexpr int kGtStages = 4;
+constexpr int kGtMaxZ = 32;
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// UMMA shared-memory descriptor for an MN-major operand tile made of 64-wide MN groups, each group = [k rows x 128 B]
+// written by TMA SWIZZLE_128B: canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units, i.e.
+// LBO = byte distance between MN groups, SBO = 1024 (eight 128-byte k rows).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t group_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((group_bytes >> 4) & 0x3FFFu) << 16) | (64ull << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+// how (mn0, k, z) of a tile becomes TMA coordinates {inner, row, batch}
+struct TcOperand {
+  int mn_major;   // 0: global [mn rows][k cols] (K-major);  1: global [k rows][mn cols] (MN-major)
+  int kmod;       // > 0: the reduction index runs over the batch dim too: k -> (k % kmod, batch += k / kmod)
+  int zmul;       // batch coordinate = blockIdx.z * zmul (+ k / kmod)
+};
+
+enum TcEpi {
+  TE_STORE = 0,   // out[z][r, c] = acc (+ bias[z][c]), fp32, masked to M x N
+  TE_IN,          // h0 = acc + b -> o0 ; a0 = h0 (1+g) + beta -> b0
+  TE_W1,          // z1 = acc + b -> o0 ; u = silu(z1) -> b0
+  TE_W2,          // z2 = f0 + acc + b -> o0 ; h = silu(z2) -> o1 ; FiLM(h; f1) or h -> b0
+  TE_HEAD,        // logits = acc + b -> o0 ; CE loss part -> o1[cta] ; dlogits -> b0 [B,32]
+  TE_BHEAD,       // dz2 = acc * silu'(f0) -> o0 (fp32 residual grad), b0
+  TE_BW2,         // dz1 = acc * silu'(f0) -> b0
+  TE_BW1,         // da = acc: dgb -> b1 ; dh = f3 + da (1+g) ; (dz2_prev = dh silu'(f2) -> o0, b0) or (dh0 -> b0)
+  TE_DCOND        // acc scattered: atomicAdd into time_emb / basis_emb gradient rows
+};
+
+struct TcGemm {
+  int M, N, K;
+  TcOperand a, b;
+  // epilogue slots (meaning per TcEpi above)
+  const float* bias; int64_t bias_zstride;
+  const float *f0, *f1, *f2, *f3;
+  float *o0, *o1;
+  __nv_bfloat16 *b0, *b1;
+  const int32_t *i0, *i1;
+  const uint16_t* x0;
+  int64_t ld;          // leading dim of [rows, H]-shaped arrays and of TE_STORE's output
+  int64_t ldg;         // leading dim of FiLM-shaped arrays (2H)
+  int64_t out_zoff[kGtMaxZ];
+  int nq, E, flag;     // qubits (TE_HEAD), embed dim (TE_DCOND), variant flag (TE_W2: 1 = FiLM next, TE_BW1: 1 = l > 0)
+  float scale;         // TE_HEAD: loss_scale / (B*N)
+};
+
+template <int BN>
+__host__ __device__ constexpr int gt_stage_bytes() { return 16384 + BN * 128; }
+template <int BN>
+__host__ __device__ constexpr int gt_smem_bytes() { return 1024 + kGtStages * gt_stage_bytes<BN>() + 256; }
+
+__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float dsilu_fast(float v) { float s = sigmoid_fast(v); return s * (1.0f + v * (1.0f - s)); }
+
+__device__ __forceinline__ void ld32(const float* p, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 t = reinterpret_cast<const float4*>(p)[i];
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void st32(float* p, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void st32_bf16(__nv_bfloat16* p, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    reinterpret_cast<uint4*>(p)[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                                pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGtThreads)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcGemm G) {
+  constexpr int STAGE = gt_stage_bytes<BN>();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + kGtStages * STAGE);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kGtStages + 1);
+  float* s_red = (float*)(tmem_slot + 4);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kGtStages), bar_acc = smem_u32(bars + 2 * kGtStages);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN, z = blockIdx.z;
+  const int KB = (G.K + 63) >> 6;
+
+  if (tid == 0) {
+    for (int i = 0; i < kGtStages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *((volatile uint32_t*)tmem_slot);
+
+  if (warp == 4) {
+    // =============================== TMA producer ===============================
+    const uint32_t elected = elect_one();
+    if (elected) { tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); }
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % kGtStages;
+      const uint32_t ph = (uint32_t)(kb / kGtStages) & 1u;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1u, 40);
+      if (elected) {
+        const uint32_t full = bar_full + 8 * s;
+        const uint32_t dstA = smem_u32(smem + s * STAGE), dstB = dstA + 16384;
+        mbar_expect_tx(full, (uint32_t)STAGE);
+        const int kg = kb * 64;
+        int ka = kg, za = z * G.a.zmul, kbb = kg, zb = z * G.b.zmul;
+        if (G.a.kmod > 0) { za += kg / G.a.kmod; ka = kg % G.a.kmod; }
+        if (G.b.kmod > 0) { zb += kg / G.b.kmod; kbb = kg % G.b.kmod; }
+        if (G.a.mn_major) {
+          tma_load_3d(dstA, &mapA, full, m0, ka, za);
+          tma_load_3d(dstA + 8192, &mapA, full, m0 + 64, ka, za);
+        } else {
+          tma_load_3d(dstA, &mapA, full, ka, m0, za);
+        }
+        if (G.b.mn_major) {
+#pragma unroll
+          for (int g = 0; g < BN / 64; ++g) tma_load_3d(dstB + g * 8192, &mapB, full, n0 + g * 64, kbb, zb);
+        } else {
+          tma_load_3d(dstB, &mapB, full, kbb, n0, zb);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 5) {
+    // =============================== MMA issuer ===============================
+    const uint32_t elected = elect_one();
+    const uint32_t idesc = umma_idesc_bf16(BN) | ((uint32_t)(G.a.mn_major != 0) << 15) | ((uint32_t)(G.b.mn_major != 0) << 16);
+    const uint32_t a_step = G.a.mn_major ? 2048u : 32u, b_step = G.b.mn_major ? 2048u : 32u;
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % kGtStages;
+      const uint32_t ph = (uint32_t)(kb / kGtStages) & 1u;
+      mbar_wait(bar_full + 8 * s, ph, 41);
+      tc_fence_after();
+      if (elected) {
+        const uint32_t aaddr = smem_u32(smem + s * STAGE), baddr = aaddr + 16384;
+        const uint64_t ad = G.a.mn_major ? umma_desc_mn_sw128(aaddr, 8192) : umma_desc_sw128(aaddr);
+        const uint64_t bd = G.b.mn_major ? umma_desc_mn_sw128(baddr, 8192) : umma_desc_sw128(baddr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          umma_bf16(tmem_base, desc_adv(ad, j * a_step), desc_adv(bd, j * b_step), idesc, (uint32_t)((kb | j) != 0));
+        umma_commit(bar_empty + 8 * s);
+        if (kb == KB - 1) umma_commit(bar_acc);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================== epilogue: thread = output row ===============================
+    const int r = m0 + warp * 32 + lane;
+    const bool rv = r < G.M;
+    mbar_wait(bar_acc, 0, 42);
+    tc_fence_after();
+    float loss_acc = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (EPI == TE_HEAD && c0 > 0) break;
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, raw);
+      tmem_wait_ld32(raw);
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+      const int c = n0 + c0;                      // first global column of this chunk
+      if (EPI == TE_STORE) {
+        if (rv && c < G.N) {
+          float* o = G.o0 + G.out_zoff[z] + (int64_t)r * G.ld + c;
+          const float* bz = G.bias ? G.bias + (int64_t)z * G.bias_zstride + c : nullptr;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            if (c + i < G.N) {      // N is a multiple of 4
+              float4 t = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              if (bz) { t.x += bz[i]; t.y += bz[i + 1]; t.z += bz[i + 2]; t.w += bz[i + 3]; }
+              *reinterpret_cast<float4*>(o + i) = t;
+            }
+          }
+        }
+      } else if (EPI == TE_DCOND) {
+        if (rv) {
+          const int E = G.E;
+          float* gt = G.o0 + (int64_t)G.i0[r] * E;
+          float* gbs = G.o1 + (int64_t)G.i1[r] * E;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int cc = c + i;
+            if (cc < E) atomicAdd(gt + cc, v[i]);
+            else if (cc < 2 * E) atomicAdd(gbs + (cc - E), v[i]);
+          }
+        }
+      } else if (EPI == TE_HEAD) {
+        // columns [0, 2*nq) are the logits of row r (class fastest)
+        float dl[32];
+        float lrow = 0.f;
+        const uint32_t bits = rv ? G.x0[r] : 0u;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          float l0 = v[2 * q] + (q < G.nq ? G.bias[2 * q] : 0.f), l1 = v[2 * q + 1] + (q < G.nq ? G.bias[2 * q + 1] : 0.f);
+          v[2 * q] = l0; v[2 * q + 1] = l1;
+          float m = fmaxf(l0, l1), e0 = __expf(l0 - m), e1 = __expf(l1 - m), s = e0 + e1;
+          const uint32_t y = (bits >> q) & 1u;
+          const float inv = __fdividef(1.0f, s);
+          const bool on = q < G.nq;
+          lrow += on ? (m + __logf(s)) - (y ? l1 : l0) : 0.f;
+          dl[2 * q] = on ? (e0 * inv - (y ? 0.f : 1.f)) * G.scale : 0.f;
+          dl[2 * q + 1] = on ? (e1 * inv - (y ? 1.f : 0.f)) * G.scale : 0.f;
+        }
+        if (rv) {
+          loss_acc += lrow;
+          float* lo = G.o0 + (int64_t)r * (2 * G.nq);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (i < 2 * G.nq) lo[i] = v[i];
+          st32_bf16(G.b0 + (int64_t)r * 32, dl);
+        }
+      } else if (rv) {
+        const int64_t e = (int64_t)r * G.ld + c;          // element offset in [rows, H] arrays
+        if (EPI == TE_IN) {
+          float g[32], be[32];
+          ld32(G.f1 + (int64_t)r * G.ldg + c, g);
+          ld32(G.f1 + (int64_t)r * G.ldg + G.ld + c, be);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(G.bias + c + i);
+          st32(G.o0 + e, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], 1.0f + g[i], be[i]);
+          st32_bf16(G.b0 + e, v);
+        } else if (EPI == TE_W1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(G.bias + c + i);
+          st32(G.o0 + e, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= sigmoid_fast(v[i]);
+          st32_bf16(G.b0 + e, v);
+        } else if (EPI == TE_W2) {
+          float hin[32];
+          ld32(G.f0 + e, hin);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += hin[i] + __ldg(G.bias + c + i);
+          st32(G.o0 + e, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= sigmoid_fast(v[i]);
+          st32(G.o1 + e, v);
+          if (G.flag) {
+            float g[32], be[32];
+            ld32(G.f1 + (int64_t)r * G.ldg + c, g);
+            ld32(G.f1 + (int64_t)r * G.ldg + G.ld + c, be);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], 1.0f + g[i], be[i]);
+          }
+          st32_bf16(G.b0 + e, v);
+        } else if (EPI == TE_BHEAD) {
+          float zz[32];
+          ld32(G.f0 + e, zz);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= dsilu_fast(zz[i]);
+          st32(G.o0 + e, v);
+          st32_bf16(G.b0 + e, v);
+        } else if (EPI == TE_BW2) {
+          float zz[32];
+          ld32(G.f0 + e, zz);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= dsilu_fast(zz[i]);
+          st32_bf16(G.b0 + e, v);
+        } else if (EPI == TE_BW1) {
+          // v = da.  f0 = gb_l (gamma | beta), f1 = h_l, f2 = z2_{l-1}, f3 = residual gradient (dz2_l)
+          float t[32], w[32];
+          ld32(G.f1 + e, t);                                   // h_in
+#pragma unroll
+          for (int i = 0; i < 32; ++i) w[i] = v[i] * t[i];      // dgamma = da * h_in
+          st32_bf16(G.b1 + (int64_t)r * G.ldg + c, w);
+          st32_bf16(G.b1 + (int64_t)r * G.ldg + G.ld + c, v);   // dbeta = da
+          ld32(G.f0 + (int64_t)r * G.ldg + c, t);               // gamma
+          ld32(G.f3 + e, w);                                    // residual gradient
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], 1.0f + t[i], w[i]);
+          if (G.flag) {
+            ld32(G.f2 + e, t);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= dsilu_fast(t[i]);
+            st32(G.o0 + e, v);
+          }
+          st32_bf16(G.b0 + e, v);
+        }
+      }
+    }
+    if (EPI == TE_HEAD) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xFFFFFFFFu, loss_acc, o);
+      if (lane == 0) s_red[warp] = loss_acc;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid == 0) G.o1[blockIdx.x] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ small CUDA-core kernels
+// xin = token embeddings (variant B), cond = [time_emb[t] | basis_emb[basis]], ind[b, v*N+q] = (bit_q == v); all bf16
+__global__ void gather_tc_kernel(int N, int E, const float* __restrict__ x_emb, const float* __restrict__ time_emb,
+                                 const float* __restrict__ basis_emb, const uint16_t* __restrict__ xt,
+                                 const int32_t* __restrict__ t, const int32_t* __restrict__ basis,
+                                 __nv_bfloat16* __restrict__ xin, __nv_bfloat16* __restrict__ cond, __nv_bfloat16* __restrict__ ind) {
+  const int64_t i = blockIdx.x;
+  const uint32_t bits = xt[i];
+  const float* te = time_emb + (int64_t)t[i] * E;
+  const float* be = basis_emb + (int64_t)basis[i] * E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    cond[i * 2 * E + e] = __float2bfloat16(te[e]);
+    cond[i * 2 * E + E + e] = __float2bfloat16(be[e]);
+  }
+  for (int j = threadIdx.x; j < N * E; j += blockDim.x) {
+    int q = j / E, e = j - q * E;
+    xin[i * N * E + j] = __float2bfloat16(x_emb[((bits >> q) & 1u) * E + e]);
+  }
+  if (threadIdx.x < 32) {
+    int j = threadIdx.x, v = j / N, q = j - v * N;
+    float f = (j < 2 * N && ((bits >> q) & 1u) == (uint32_t)v) ? 1.f : 0.f;
+    ind[i * 32 + j] = __float2bfloat16(f);
+  }
+}
+
+__global__ void loss_finish_tc_kernel(const float* __restrict__ part, int n, float inv_total, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { double s = 0.0; for (int i = 0; i < n; ++i) s += part[i]; out[0] = (float)(s * inv_total); }
+}
+
+// bias gradients: deterministic column sums of the bf16 dY arrays
+struct ColsumTask { const __nv_bfloat16* p; int64_t ld; int cols; float* out; };
+struct ColsumTasks { ColsumTask t[56]; };
+__global__ void colsum_bf16_kernel(const __grid_constant__ ColsumTasks T, int64_t rows) {
+  const ColsumTask k = T.t[blockIdx.y];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
+  if (blockIdx.x * 64 >= k.cols) return;
+  __shared__ float red[8][64];
+  const int w = threadIdx.x >> 5;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < k.cols) {
+    for (int64_t r = w; r < rows; r += 8) {
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(k.p + r * k.ld + c);
+      a0 += bf16_lo(u); a1 += bf16_hi(u);
+    }
+  }
+  red[w][(threadIdx.x & 31) * 2] = a0; red[w][(threadIdx.x & 31) * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < k.cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    k.out[blockIdx.x * 64 + threadIdx.x] = s;
+  }
+}
+
+// x_emb gradient from S[v*N+q, h] = sum_b [bit_q(b) == v] dh0[b, h]:  g[v, e] = sum_q sum_h S[vN+q, h] Win[h, qE+e]
+__global__ void xemb_grad_kernel(int N, int E, int H, const float* __restrict__ S, const float* __restrict__ in_w,
+                                 float* __restrict__ g_xemb) {
+  const int q = blockIdx.x, h0 = blockIdx.y * 64;
+  for (int j = threadIdx.x; j < 2 * E; j += blockDim.x) {
+    const int v = j / E, e = j - v * E;
+    const float* s = S + (int64_t)(v * N + q) * H + h0;
+    const float* w = in_w + (int64_t)h0 * (N * E) + q * E + e;
+    float acc = 0.f;
+    for (int h = 0; h < 64; ++h) acc = fmaf(s[h], w[(int64_t)h * (N * E)], acc);
+    atomicAdd(g_xemb + j, acc);
+  }
+}
+
+// torch Adam / AdamW arithmetic (same as train.cu's adam_kernel) with the step count read from device memory (so
+// the whole training step can be replayed from a CUDA graph) and a bf16 shadow of the updated parameters.
+__global__ void adam_tc_kernel(float* __restrict__ p, __nv_bfloat16* __restrict__ shadow, const float* __restrict__ g,
+                               float* __restrict__ m, float* __restrict__ v, int64_t n, const int64_t* __restrict__ step_dev,
+                               float lr, float b1, float b2, float eps, float wd, int decoupled, float gscale) {
+  __shared__ float s_bc1, s_bc2s;
+  if (threadIdx.x == 0) {
+    const double st = (double)(step_dev[0] + 1);
+    s_bc1 = (float)(1.0 - pow((double)b1, st));
+    s_bc2s = (float)sqrt(1.0 - pow((double)b2, st));
+  }
+  __syncthreads();
+  const float bc1 = s_bc1, bc2_sqrt = s_bc2s;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float grad = g[i] * gscale, param = p[i];
+  if (decoupled) param *= (1.0f - lr * wd);
+  else if (wd != 0.f) grad += wd * param;
+  float mi = m[i] + (grad - m[i]) * (1.0f - b1);
+  float vi = v[i] * b2 + (1.0f - b2) * grad * grad;
+  m[i] = mi; v[i] = vi;
+  float denom = sqrtf(vi) / bc2_sqrt + eps;
+  param = param - (lr / bc1) * (mi / denom);
+  p[i] = param;
+  if (shadow) shadow[i] = __float2bfloat16(param);
+}
+__global__ void step_inc_kernel(int64_t* step_dev) { if (threadIdx.x == 0 && blockIdx.x == 0) step_dev[0] += 1; }
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16(src[i]);
+}
+
+// ------------------------------------------------------------------------------------ host side
+// bf16 tensor {inner, rows, batch}; box {64, box_rows, 1}; 128-byte swizzle; out-of-bounds elements read as zero
+static int make_map3(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, int64_t batch, int64_t row_stride,
+                     int64_t batch_stride, int box_rows) {
+  EncodeTiledFn fn;
+  DDQST_TRY(get_encode_fn(&fn));
+  DDQST_REQUIRE(((uintptr_t)base & 15u) == 0 && (row_stride * 2) % 16 == 0 && (batch_stride * 2) % 16 == 0, DDQST_EUNSUPPORTED,
+                "tensor-core training needs 16-byte aligned operands (base %p, row stride %lld, batch stride %lld elements)",
+                base, (long long)row_stride, (long long)batch_stride);
+  cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t gstride[2] = {(cuuint64_t)row_stride * 2, (cuuint64_t)batch_stride * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DDQST_REQUIRE(r == CUDA_SUCCESS, DDQST_ECUDA, "cuTensorMapEncodeTiled(3d) failed with CUresult %d (inner=%lld rows=%lld batch=%lld)",
+                (int)r, (long long)inner, (long long)rows, (long long)batch);
+  return DDQST_OK;
+}
+
+// one operand of a GEMM as the host describes it: the matrix [mn, k] per batch entry, stored either way round
+struct HostOperand {
+  const void* base; int mn_major; int64_t mn, k, batch, ld, batch_stride; int kmod, zmul;
+};
+static HostOperand op_k(const void* base, int64_t mn, int64_t k, int64_t ld) { return HostOperand{base, 0, mn, k, 1, ld, mn * ld, 0, 0}; }
+static HostOperand op_mn(const void* base, int64_t mn, int64_t k, int64_t ld) { return HostOperand{base, 1, mn, k, 1, ld, k * ld, 0, 0}; }
+
+template <int BN, int EPI>
+static int launch_gemm_bn(const HostOperand& A, const HostOperand& B, TcGemm g, int zcount, cudaStream_t s) {
+  CUtensorMap ma, mb;
+  if (A.mn_major) DDQST_TRY(make_map3(&ma, A.base, A.mn, A.k, A.batch, A.ld, A.batch_stride, 64));
+  else DDQST_TRY(make_map3(&ma, A.base, A.k, A.mn, A.batch, A.ld, A.batch_stride, 128));
+  if (B.mn_major) DDQST_TRY(make_map3(&mb, B.base, B.mn, B.k, B.batch, B.ld, B.batch_stride, 64));
+  else DDQST_TRY(make_map3(&mb, B.base, B.k, B.mn, B.batch, B.ld, B.batch_stride, BN));
+  g.a = TcOperand{A.mn_major, A.kmod, A.zmul};
+  g.b = TcOperand{B.mn_major, B.kmod, B.zmul};
+  static bool attr_set = false;
+  if (!attr_set) {
+    DDQST_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes<BN>()));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((g.M + 127) / 128), (unsigned)((g.N + BN - 1) / BN), (unsigned)zcount);
+  gemm_tc_kernel<BN, EPI><<<grid, kGtThreads, gt_smem_bytes<BN>(), s>>>(ma, mb, g);
+  DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
+
+// BN = 128 when the grid still covers the machine (or N is not a multiple of 64-wide tiles anyway), else 64
+template <int EPI>
+static int launch_gemm(const HostOperand& A, const HostOperand& B, const TcGemm& g, int zcount, cudaStream_t s) {
+  const int64_t tiles128 = (int64_t)((g.M + 127) / 128) * ((g.N + 127) / 128) * zcount;
+  const bool fused = EPI != TE_STORE && EPI != TE_DCOND && EPI != TE_HEAD;
+  const bool can128 = !fused || g.N % 128 == 0;
+  if (can128 && EPI != TE_HEAD && tiles128 >= 96) return launch_gemm_bn<128, EPI>(A, B, g, zcount, s);
+  return launch_gemm_bn<64, EPI>(A, B, g, zcount, s);
+}
+
+// ---- workspace
+struct TcWs {
+  // bf16 (element offsets into the bf16 region), fp32 (element offsets into the fp32 region)
+  int64_t xin, cond, ind, act, hL, dz, dgb, dh0, dlog, bf_total;
+  int64_t gb, h, z1, z2, logits, dres, S, loss_part, f_total;
+};
+static void tc_ws_layout(const ddqst_dims* d, int64_t B, TcWs* w) {
+  const int64_t N = d->num_qubits, E = d->embed_dim, H = d->hidden_dim, L = d->num_blocks;
+  int64_t off = 0;
+  auto take = [&](int64_t n) { int64_t o = off; off = align_up(off + n, 128); return o; };
+  w->xin = take(B * N * E); w->cond = take(B * 2 * E); w->ind = take(B * 32); w->act = take(2 * L * B * H); w->hL = take(B * H);
+  w->dz = take(2 * L * B * H); w->dgb = take(L * B * 2 * H); w->dh0 = take(B * H); w->dlog = take(B * 32);
+  w->bf_total = off;
+  off = 0;
+  w->gb = take(L * B * 2 * H); w->h = take((L + 1) * B * H); w->z1 = take(L * B * H); w->z2 = take(L * B * H);
+  w->logits = take(B * 2 * N); w->dres = take(B * H); w->S = take(32 * H); w->loss_part = take((B + 127) / 128 + 8);
+  w->f_total = off;
+}
+
+int64_t train_tc_workspace_bytes(const ddqst_dims* d, int64_t batch) {
+  if (validate_dims(d) != DDQST_OK) return -1;
+  TcWs w;
+  tc_ws_layout(d, batch < 1 ? 1 : batch, &w);
+  return w.bf_total * 2 + w.f_total * 4 + 1024;
+}
+
+int train_tc_abort_fetch() { return tc_abort_fetch(); }
+
+static int train_tc_supported(const ddqst_dims* d, const ParamLayout& pr) {
+  DDQST_REQUIRE(d->variant == DDQST_VARIANT_B, DDQST_EUNSUPPORTED,
+                "tensor-core training is built for the RQC model variant (x_emb front end); use precision fp32 for variant A");
+  DDQST_REQUIRE(d->hidden_dim % 64 == 0 && d->embed_dim % 16 == 0 && d->num_qubits <= 15 && 2 * d->num_blocks <= kGtMaxZ,
+                DDQST_EUNSUPPORTED, "tensor-core training needs hidden_dim %% 64 == 0, embed_dim %% 16 == 0, num_qubits <= 15, num_blocks <= 16");
+  bool ok = pr.in_w % 8 == 0 && pr.head_w % 8 == 0;
+  for (int l = 0; l < d->num_blocks; ++l) ok = ok && pr.film_w[l] % 8 == 0 && pr.w1[l] % 8 == 0 && pr.w2[l] % 8 == 0;
+  DDQST_REQUIRE(ok, DDQST_EUNSUPPORTED, "parameter offsets are not 16-byte aligned in the bf16 shadow");
+  return DDQST_OK;
+}
+
+static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfloat16* shadow, const uint16_t* xt,
+                        const uint16_t* x0, const int32_t* t, const int32_t* basis, int64_t B, float loss_scale,
+                        float* grads, float* loss_out, void* workspace, int64_t ws_bytes, cudaStream_t s) {
+  ParamLayout pr;
+  DDQST_TRY(param_layout(d, &pr));
+  DDQST_TRY(train_tc_supported(d, pr));
+  TcWs w;
+  tc_ws_layout(d, B, &w);
+  DDQST_REQUIRE(workspace && ws_bytes >= w.bf_total * 2 + w.f_total * 4 + 1024, DDQST_EWORKSPACE,
+                "tensor-core train step needs %lld workspace bytes, got %lld", (long long)(w.bf_total * 2 + w.f_total * 4 + 1024), (long long)ws_bytes);
+  const int N = d->num_qubits, E = d->embed_dim, H = d->hidden_dim, L = d->num_blocks, XIN = N * E;
+  char* base = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  __nv_bfloat16* bf = (__nv_bfloat16*)base;
+  float* fp = (float*)(base + align_up(w.bf_total * 2, 1024));
+  __nv_bfloat16 *xin = bf + w.xin, *cond = bf + w.cond, *ind = bf + w.ind, *act = bf + w.act, *hL = bf + w.hL, *dz = bf + w.dz,
+                *dgb = bf + w.dgb, *dh0 = bf + w.dh0, *dlog = bf + w.dlog;
+  float *gb = fp + w.gb, *h = fp + w.h, *z1 = fp + w.z1, *z2 = fp + w.z2, *logits = fp + w.logits, *dres = fp + w.dres,
+        *S = fp + w.S, *loss_part = fp + w.loss_part;
+  const int64_t BH = B * H, BG = B * 2 * H;
+  const int64_t blk_stride = L > 1 ? pr.film_w[1] - pr.film_w[0] : 0;
+
+  auto base_gemm = [&](int M, int Nn, int K) {
+    TcGemm g{};
+    g.M = M; g.N = Nn; g.K = K; g.ld = H; g.ldg = 2 * H; g.E = E; g.nq = N;
+    return g;
+  };
+
+  gather_tc_kernel<<<(unsigned)B, 128, 0, s>>>(N, E, params + pr.x_emb, params + pr.time_emb, params + pr.basis_emb, xt, t, basis,
+                                               xin, cond, ind);
+  DDQST_LAUNCH_OK();
+
+  // ------------------------------------------------------------------ forward
+  {  // gb[l] = cond . Wfilm_l^T + bfilm_l, all blocks in one launch
+    TcGemm g = base_gemm((int)B, 2 * H, 2 * E);
+    g.o0 = gb; g.ld = 2 * H; g.bias = params + pr.film_b[0]; g.bias_zstride = blk_stride;
+    for (int l = 0; l < L; ++l) g.out_zoff[l] = (int64_t)l * BG;
+    HostOperand A = op_k(cond, B, 2 * E, 2 * E);
+    HostOperand Bo{shadow + pr.film_w[0], 0, 2 * H, 2 * E, L, 2 * E, blk_stride > 0 ? blk_stride : (int64_t)2 * H * 2 * E, 0, 1};
+    DDQST_TRY(launch_gemm<TE_STORE>(A, Bo, g, L, s));
+  }
+  {  // h0, a0
+    TcGemm g = base_gemm((int)B, H, XIN);
+    g.bias = params + pr.in_b; g.o0 = h; g.f1 = gb; g.b0 = act;
+    DDQST_TRY(launch_gemm<TE_IN>(op_k(xin, B, XIN, XIN), op_k(shadow + pr.in_w, H, XIN, XIN), g, 1, s));
+  }
+  for (int l = 0; l < L; ++l) {
+    {
+      TcGemm g = base_gemm((int)B, H, H);
+      g.bias = params + pr.b1[l]; g.o0 = z1 + l * BH; g.b0 = act + (2 * l + 1) * BH;
+      DDQST_TRY(launch_gemm<TE_W1>(op_k(act + 2 * l * BH, B, H, H), op_k(shadow + pr.w1[l], H, H, H), g, 1, s));
+    }
+    {
+      TcGemm g = base_gemm((int)B, H, H);
+      g.bias = params + pr.b2[l]; g.f0 = h + l * BH; g.o0 = z2 + l * BH; g.o1 = h + (l + 1) * BH;
+      g.flag = l + 1 < L; g.f1 = gb + (int64_t)(l + 1) * BG; g.b0 = l + 1 < L ? act + 2 * (l + 1) * BH : hL;
+      DDQST_TRY(launch_gemm<TE_W2>(op_k(act + (2 * l + 1) * BH, B, H, H), op_k(shadow + pr.w2[l], H, H, H), g, 1, s));
+    }
+  }
+  const int head_ctas = (int)((B + 127) / 128);
+  {  // logits, loss parts, dlogits
+    TcGemm g = base_gemm((int)B, 2 * N, H);
+    g.bias = params + pr.head_b; g.o0 = logits; g.o1 = loss_part; g.b0 = dlog; g.x0 = x0;
+    g.scale = loss_scale / (float)(B * N);
+    DDQST_TRY(launch_gemm<TE_HEAD>(op_k(hL, B, H, H), op_k(shadow + pr.head_w, 2 * N, H, H), g, 1, s));
+  }
+  loss_finish_tc_kernel<<<1, 32, 0, s>>>(loss_part, head_ctas, 1.0f / (float)(B * N), loss_out);
+  DDQST_LAUNCH_OK();
+
+  // ------------------------------------------------------------------ backward: data gradients
+  // embedding gradients are accumulated with atomics; the alignment padding between tensors must read as zero too
+  DDQST_CUDA_OK(cudaMemsetAsync(grads, 0, sizeof(float) * pr.total, s));
+  {  // dz2_{L-1} = (dlogits . Whead) * silu'(z2_{L-1})
+    TcGemm g = base_gemm((int)B, H, 2 * N);
+    g.f0 = z2 + (L - 1) * BH; g.o0 = dres; g.b0 = dz + (2 * (L - 1) + 1) * BH;
+    DDQST_TRY(launch_gemm<TE_BHEAD>(op_k(dlog, B, 2 * N, 32), op_mn(shadow + pr.head_w, H, 2 * N, H), g, 1, s));
+  }
+  for (int l = L - 1; l >= 0; --l) {
+    {  // dz1_l = (dz2_l . W2_l) * silu'(z1_l)
+      TcGemm g = base_gemm((int)B, H, H);
+      g.f0 = z1 + l * BH; g.b0 = dz + 2 * l * BH;
+      DDQST_TRY(launch_gemm<TE_BW2>(op_k(dz + (2 * l + 1) * BH, B, H, H), op_mn(shadow + pr.w2[l], H, H, H), g, 1, s));
+    }
+    {  // da_l = dz1_l . W1_l -> dgb_l, dh_l -> dz2_{l-1} or dh0
+      TcGemm g = base_gemm((int)B, H, H);
+      g.f0 = gb + (int64_t)l * BG; g.f1 = h + l * BH; g.f3 = dres; g.b1 = dgb + (int64_t)l * BG;
+      g.flag = l > 0;
+      if (l > 0) { g.f2 = z2 + (l - 1) * BH; g.o0 = dres; g.b0 = dz + (2 * (l - 1) + 1) * BH; }
+      else g.b0 = dh0;
+      DDQST_TRY(launch_gemm<TE_BW1>(op_k(dz + 2 * l * BH, B, H, H), op_mn(shadow + pr.w1[l], H, H, H), g, 1, s));
+    }
+  }
+  {  // dcond = sum_l dgb_l . Wfilm_l, scattered into the time / basis embedding gradients
+    TcGemm g = base_gemm((int)B, 2 * E, L * 2 * H);
+    g.o0 = grads + pr.time_emb; g.o1 = grads + pr.basis_emb; g.i0 = t; g.i1 = basis;
+    HostOperand A{dgb, 0, B, 2 * H, L, 2 * H, BG, 2 * H, 0};
+    HostOperand Bo{shadow + pr.film_w[0], 1, 2 * E, 2 * H, L, 2 * E, blk_stride > 0 ? blk_stride : (int64_t)2 * H * 2 * E, 2 * H, 0};
+    DDQST_TRY(launch_gemm<TE_DCOND>(A, Bo, g, 1, s));
+  }
+  // ------------------------------------------------------------------ backward: weight gradients (dY^T . X over the batch)
+  {  // W1_l, W2_l for every block: z = 2l (dz1_l, a_l), 2l+1 (dz2_l, u_l)
+    TcGemm g = base_gemm(H, H, (int)B);
+    g.o0 = grads;
+    for (int l = 0; l < L; ++l) { g.out_zoff[2 * l] = pr.w1[l]; g.out_zoff[2 * l + 1] = pr.w2[l]; }
+    HostOperand A{dz, 1, H, B, 2 * L, H, BH, 0, 1};
+    HostOperand Bo{act, 1, H, B, 2 * L, H, BH, 0, 1};
+    DDQST_TRY(launch_gemm<TE_STORE>(A, Bo, g, 2 * L, s));
+  }
+  {  // Wfilm_l
+    TcGemm g = base_gemm(2 * H, 2 * E, (int)B);
+    g.o0 = grads; g.ld = 2 * E;
+    for (int l = 0; l < L; ++l) g.out_zoff[l] = pr.film_w[l];
+    HostOperand A{dgb, 1, 2 * H, B, L, 2 * H, BG, 0, 1};
+    HostOperand Bo{cond, 1, 2 * E, B, 1, 2 * E, B * 2 * E, 0, 0};
+    DDQST_TRY(launch_gemm<TE_STORE>(A, Bo, g, L, s));
+  }
+  {  // Win
+    TcGemm g = base_gemm(H, XIN, (int)B);
+    g.o0 = grads + pr.in_w; g.ld = XIN;
+    DDQST_TRY(launch_gemm<TE_STORE>(op_mn(dh0, H, B, H), op_mn(xin, XIN, B, XIN), g, 1, s));
+  }
+  {  // Whead
+    TcGemm g = base_gemm(2 * N, H, (int)B);
+    g.o0 = grads + pr.head_w; g.ld = H;
+    DDQST_TRY(launch_gemm<TE_STORE>(op_mn(dlog, 2 * N, B, 32), op_mn(hL, H, B, H), g, 1, s));
+  }
+  {  // S = ind^T . dh0  (for the x_emb gradient)
+    TcGemm g = base_gemm(2 * N, H, (int)B);
+    g.o0 = S; g.ld = H;
+    DDQST_TRY(launch_gemm<TE_STORE>(op_mn(ind, 2 * N, B, 32), op_mn(dh0, H, B, H), g, 1, s));
+  }
+  // ------------------------------------------------------------------ bias gradients, x_emb gradient
+  {
+    ColsumTasks T{};
+    int n = 0, maxc = 0;
+    auto add = [&](const __nv_bfloat16* p, int64_t ld, int cols, float* out) { T.t[n++] = ColsumTask{p, ld, cols, out}; if (cols > maxc) maxc = cols; };
+    for (int l = 0; l < L; ++l) {
+      add(dz + 2 * l * BH, H, H, grads + pr.b1[l]);
+      add(dz + (2 * l + 1) * BH, H, H, grads + pr.b2[l]);
+      add(dgb + (int64_t)l * BG, 2 * H, 2 * H, grads + pr.film_b[l]);
+    }
+    add(dh0, H, H, grads + pr.in_b);
+    add(dlog, 32, 2 * N, grads + pr.head_b);
+    colsum_bf16_kernel<<<dim3((unsigned)((maxc + 63) / 64), (unsigned)n), 256, 0, s>>>(T, B);
+    DDQST_LAUNCH_OK();
+  }
+  xemb_grad_kernel<<<dim3((unsigned)N, (unsigned)(H / 64)), 128, 0, s>>>(N, E, H, S, params + pr.in_w, grads + pr.x_emb);
+  DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
+
+}  // namespace ddqst
+
+using namespace ddqst;
+
+extern "C" {
+
+int ddqst_cast_bf16(const float* src, uint16_t* dst, int64_t n, void* stream) {
+  DDQST_TRY(check_arch());
+  DDQST_REQUIRE(n >= 0 && (n == 0 || (src && dst)), DDQST_EINVAL_SHAPE, "bad argument");
+  if (n == 0) return DDQST_OK;
+  cast_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
+
+int ddqst_train_forward_backward_tc(const ddqst_dims* d, const float* params, const uint16_t* params_bf16,
+                                    const uint16_t* xt_packed, const uint16_t* x0_packed, const int32_t* t,
+                                    const int32_t* basis, int64_t batch, float loss_scale, float* grads, float* loss_out,
+                                    void* workspace, int64_t ws_bytes, void* stream) {
+  DDQST_TRY(check_arch());
+  DDQST_TRY(validate_dims(d));
+  DDQST_REQUIRE(batch >= 1, DDQST_EINVAL_SHAPE, "batch=%lld", (long long)batch);
+  DDQST_REQUIRE(params && params_bf16 && xt_packed && x0_packed && t && basis && grads && loss_out, DDQST_EINVAL_SHAPE, "NULL argument");
+  return train_tc_run(d, params, (const __nv_bfloat16*)params_bf16, xt_packed, x0_packed, t, basis, batch, loss_scale, grads,
+                      loss_out, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+int ddqst_adam_step_dev(float* params, uint16_t* params_bf16, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        int64_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled,
+                        float grad_scale, void* stream) {
+  DDQST_TRY(check_arch());
+  DDQST_REQUIRE(n >= 0 && step_dev, DDQST_EINVAL_SHAPE, "n=%lld", (long long)n);
+  if (n > 0) {
+    DDQST_REQUIRE(params && grads && exp_avg && exp_avg_sq, DDQST_EINVAL_SHAPE, "NULL argument");
+    adam_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, (__nv_bfloat16*)params_bf16, grads, exp_avg,
+                                                                                 exp_avg_sq, n, step_dev, lr, beta1, beta2, eps,
+                                                                                 weight_decay, decoupled, grad_scale);
+    DDQST_LAUNCH_OK();
+  }
+  step_inc_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_dev);
+  DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
+
+// C[z][M,N] fp32 = A . B^T over bf16 operands given in either storage order (self test of the training GEMM kernel):
+// a_mn == 0: A is [M,K] row-major, else [K,M]; b_mn == 0: B is [N,K] row-major, else [K,N].
+int ddqst_selftest_gemm_tc(const uint16_t* a, const uint16_t* b, int a_mn, int b_mn, int32_t m, int32_t n, int32_t k,
+                           int32_t batch, float* c, void* stream) {
+  DDQST_TRY(check_arch());
+  DDQST_REQUIRE(m >= 1 && n >= 4 && n % 4 == 0 && k >= 1 && batch >= 1 && batch <= kGtMaxZ, DDQST_EINVAL_SHAPE, "selftest shape");
+  TcGemm g{};
+  g.M = m; g.N = n; g.K = k; g.o0 = c; g.ld = n;
+  for (int z = 0; z < batch; ++z) g.out_zoff[z] = (int64_t)z * m * n;
+  HostOperand A = a_mn ? HostOperand{a, 1, m, k, batch, m, (int64_t)k * m, 0, 1} : HostOperand{a, 0, m, k, batch, k, (int64_t)m * k, 0, 1};
+  HostOperand B = b_mn ? HostOperand{b, 1, n, k, batch, n, (int64_t)k * n, 0, 1} : HostOperand{b, 0, n, k, batch, k, (int64_t)n * k, 0, 1};
+  return launch_gemm<TE_STORE>(A, B, g, batch, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -58,15 +58,57 @@ class NativeAdam:
         self.exp_avg = torch.zeros_like(model.flat_params)
         self.exp_avg_sq = torch.zeros_like(model.flat_params)
         self.step_count = 0
+        self._step_dev = None
+
+    @property
+    def step_dev(self) -> torch.Tensor:
+        """Count of completed steps in device memory (int64[1]); read by the graph-replayable kernels."""
+        p = self.model.flat_params
+        if self._step_dev is None or self._step_dev.device != p.device:
+            self._step_dev = torch.full((1,), self.step_count, dtype=torch.int64, device=p.device)
+        return self._step_dev
+
+    def step_device(self, grads: torch.Tensor, grad_scale: float = 1.0, shadow: torch.Tensor | None = None):
+        """The same update with the step count read from (and incremented in) device memory and an optional bf16
+        shadow of the new parameters: replayable from a CUDA graph (ddqst_adam_step_dev)."""
+        lib = _lib.load()
+        p = self.model.flat_params
+        sd = self.step_dev
+        _lib.check(lib.ddqst_adam_step_dev(_lib.ptr(p), _lib.ptr(shadow), _lib.ptr(grads), _lib.ptr(self.exp_avg),
+                                           _lib.ptr(self.exp_avg_sq), p.numel(), _lib.ptr(sd), self.lr, self.betas[0],
+                                           self.betas[1], self.eps, self.weight_decay, int(self.decoupled), grad_scale,
+                                           _lib.stream_ptr()))
+        self.step_count += 1
+        self.model.native_version += 1
+        if shadow is not None:
+            self.model.mark_shadow_current()
 
     def step(self, grads: torch.Tensor, grad_scale: float = 1.0):
         lib = _lib.load()
+        if self._step_dev is not None:
+            return self.step_device(grads, grad_scale)       # keep the device-side counter authoritative once it exists
         self.step_count += 1
         p = self.model.flat_params
         _lib.check(lib.ddqst_adam_step(_lib.ptr(p), _lib.ptr(grads), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
                                        p.numel(), self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
                                        self.weight_decay, int(self.decoupled), grad_scale, _lib.stream_ptr()))
         self.model.native_version += 1
+
+
+class TrainGraph:
+    """A captured tensor-core training step (DiscreteDiffusion.make_train_graph).  ``replay()`` runs one step on whatever
+    the static input buffers hold now and returns the loss (device scalar, overwritten by the next replay)."""
+
+    def __init__(self, graph, loss, diffusion, optimizer):
+        self.graph, self.loss, self.diffusion, self.optimizer = graph, loss, diffusion, optimizer
+
+    def replay(self):
+        self.graph.replay()
+        self.optimizer.step_count += 1
+        self.diffusion._train_steps += 1
+        self.diffusion.model.native_version += 1      # packed inference tables are stale now
+        self.diffusion.model.mark_shadow_current()    # ... but the bf16 shadow was updated by the captured Adam
+        return self.loss
 
 
 class DiscreteDiffusion:
@@ -192,11 +234,22 @@ class DiscreteDiffusion:
         return unpack_bits(out, N), logits
 
     # ------------------------------------------------------------------ training step (T1)
+    def train_precision(self) -> str:
+        """'bf16' (tcgen05 GEMMs, ddqst_train_forward_backward_tc) when this object samples in bf16 and the model is the
+        RQC variant with tensor-core-friendly dims, else 'fp32' (CUDA-core exact path)."""
+        m = self.model
+        ok = (self.precision == "bf16" and m.variant == "B" and m.hidden_dim % 64 == 0 and m.embed_dim % 16 == 0
+              and m.num_qubits <= 15 and m.num_blocks <= 16)
+        return "bf16" if ok else "fp32"
+
     def train_step(self, x_0: torch.Tensor, basis: torch.Tensor, optimizer: NativeAdam, row_offset: int = 0,
-                   process_group=None):
+                   process_group=None, precision: str | None = None):
         """One step of RQC/main.py:105-115 fused: t ~ U{1..T}, x_t = q_sample(x_0, t), logits, mean cross-entropy,
-        backward, (all-reduce of the flat gradient when a process group is given,) Adam.  Returns the loss (device scalar)."""
+        backward, (all-reduce of the flat gradient when a process group is given,) Adam.  Returns the loss (device scalar).
+        ``precision`` 'bf16' runs every GEMM on the tensor cores, 'fp32' the exact CUDA-core path (default: train_precision())."""
         self._require_cuda()
+        if (precision or self.train_precision()) == "bf16":
+            return self._train_step_tc(x_0, basis, optimizer, row_offset, process_group)
         lib = _lib.load()
         m = self.model
         N = m.num_qubits
@@ -227,3 +280,62 @@ class DiscreteDiffusion:
             scale = 1.0 / world
         optimizer.step(grads, grad_scale=scale)
         return self._loss
+
+    def _train_step_tc(self, x_0, basis, optimizer: NativeAdam, row_offset: int = 0, process_group=None):
+        """Tensor-core form of train_step.  Nothing here depends on host-side counters (the step count that keys the
+        noising stream and Adam's bias correction lives in ``optimizer.step_dev``), so the call can be captured in a
+        CUDA graph (see ``make_train_graph``)."""
+        lib = _lib.load()
+        m = self.model
+        N = m.num_qubits
+        x0p = x_0 if x_0.dtype == torch.uint16 else pack_bits(x_0.to(self.device), N)
+        b32 = basis if basis.dtype == torch.int32 and basis.is_cuda else basis.to(self.device).to(torch.int32).contiguous()
+        B = x0p.shape[0]
+        st = getattr(self, "_tc_state", None)
+        if st is None or st["B"] != B or st["grads"].numel() != m.flat_params.numel() or st["grads"].device != m.flat_params.device:
+            nbytes = lib.ddqst_workspace_bytes(_lib.OP_TRAIN, C.byref(m.dims), B, _lib.PRECISION_BF16)
+            if nbytes < 0:
+                _lib.check(-1)
+            st = self._tc_state = dict(
+                B=B, xt=torch.empty(B, dtype=torch.uint16, device=self.device), t=torch.empty(B, dtype=torch.int32, device=self.device),
+                grads=torch.empty_like(m.flat_params), loss=torch.zeros(1, dtype=torch.float32, device=self.device),
+                ws=torch.empty(nbytes, dtype=torch.uint8, device=self.device))
+        shadow = m.bf16_shadow()
+        _lib.check(lib.ddqst_q_sample_dev(_lib.ptr(self._q), self.num_timesteps, N, self.cumulative, _lib.ptr(x0p), None, B,
+                                          row_offset, self.seed, _lib.ptr(optimizer.step_dev), _lib.ptr(st["xt"]),
+                                          _lib.ptr(st["t"]), _lib.stream_ptr()))
+        _lib.check(lib.ddqst_train_forward_backward_tc(C.byref(m.dims), _lib.ptr(m.flat_params), _lib.ptr(shadow), _lib.ptr(st["xt"]),
+                                                       _lib.ptr(x0p), _lib.ptr(st["t"]), _lib.ptr(b32), B, 1.0, _lib.ptr(st["grads"]),
+                                                       _lib.ptr(st["loss"]), _lib.ptr(st["ws"]), st["ws"].numel(), _lib.stream_ptr()))
+        world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            world = torch.distributed.get_world_size(process_group)
+        scale = 1.0
+        if world > 1:
+            torch.distributed.all_reduce(st["grads"], group=process_group)
+            scale = 1.0 / world
+        optimizer.step_device(st["grads"], grad_scale=scale, shadow=shadow)
+        self._train_steps += 1
+        return st["loss"]
+
+    def make_train_graph(self, x0_packed: torch.Tensor, basis_i32: torch.Tensor, optimizer: NativeAdam, row_offset: int = 0):
+        """Capture one tensor-core training step on the STATIC device buffers ``x0_packed`` (uint16[B]) and ``basis_i32``
+        (int32[B]) in a CUDA graph.  Returns a ``TrainGraph``: refill the two buffers, call ``.replay()``.
+        Single-GPU form (an all-reduce would have to be captured with it)."""
+        self._require_cuda()
+        if x0_packed.dtype != torch.uint16 or basis_i32.dtype != torch.int32 or not x0_packed.is_cuda or not basis_i32.is_cuda:
+            raise ValueError("make_train_graph needs device tensors: x0_packed uint16[B], basis_i32 int32[B]")
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self._train_step_tc(x0_packed, basis_i32, optimizer, row_offset)      # warm-up: allocations, kernel attributes
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        saved = (optimizer.step_count, self._train_steps, self.model.native_version)
+        with torch.cuda.graph(graph):
+            loss = self._train_step_tc(x0_packed, basis_i32, optimizer, row_offset)
+        # capturing launched nothing: put the host-side counters back where the device-side state is
+        optimizer.step_count, self._train_steps, self.model.native_version = saved
+        self.model.mark_shadow_current()
+        return TrainGraph(graph, loss, self, optimizer)

@@ -168,6 +168,27 @@ class ConditionalD3PM(nn.Module):
             self._pack_key = key
         return self._pack
 
+    # -- bf16 shadow of the flat parameters (operands of the tensor-core training step) ---------
+    def _param_key(self):
+        return (self.flat_params.data_ptr(), self.native_version) + tuple(p._version for p, _ in self._layout)
+
+    def bf16_shadow(self) -> torch.Tensor:
+        """bf16 copy of ``flat_params`` at the same element offsets; recast when the parameters changed behind its back
+        (the fused Adam keeps it current and calls ``mark_shadow_current``)."""
+        flat = self.flat_params
+        sh = getattr(self, "_shadow", None)
+        if sh is None or sh.numel() != flat.numel() or sh.device != flat.device:
+            sh = self._shadow = torch.empty(flat.numel(), dtype=torch.bfloat16, device=flat.device)
+            self._shadow_key = None
+        key = self._param_key()
+        if self._shadow_key != key:
+            _lib.check(_lib.load().ddqst_cast_bf16(_lib.ptr(flat), _lib.ptr(sh), flat.numel(), _lib.stream_ptr()))
+            self._shadow_key = key
+        return sh
+
+    def mark_shadow_current(self):
+        self._shadow_key = self._param_key()
+
     # -- forward ---------------------------------------------------------------------------------
     def forward(self, x, t, basis_idx):
         """x[B,N] int64 in {0,1}, t[B] int64, basis_idx[B] int64 -> logits[B,N,2] fp32 (RQC/model.py:51-70)."""

@@ -111,6 +111,12 @@ int ddqst_q_sample(const float* Q, int32_t num_timesteps, int32_t num_qubits, in
                    const uint16_t* x0_packed, const int32_t* t, int64_t batch, int64_t row_offset,
                    uint64_t seed, uint32_t stream_id, uint16_t* xt_packed, int32_t* t_out, void* stream);
 
+/* the same with the stream id read from device memory (stream_id_dev[0]; the device-side step counter that
+ * ddqst_adam_step_dev increments), so a whole training step can be captured in a CUDA graph and replayed. */
+int ddqst_q_sample_dev(const float* Q, int32_t num_timesteps, int32_t num_qubits, int cumulative,
+                       const uint16_t* x0_packed, const int32_t* t, int64_t batch, int64_t row_offset,
+                       uint64_t seed, const int64_t* stream_id_dev, uint16_t* xt_packed, int32_t* t_out, void* stream);
+
 /* ---- H0: per-basis histogram of packed bitstrings (elem_bytes 1 or 2), counts ACCUMULATED into
  * hist[2^N] uint32. */
 int ddqst_histogram(const void* packed, int elem_bytes, int64_t n, int32_t num_qubits, uint32_t* hist, void* stream);
@@ -167,6 +173,23 @@ int ddqst_adam_step(float* params, const float* grads, float* exp_avg, float* ex
                     int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
                     int decoupled, float grad_scale, void* stream);
 
+/* ---- T1 on the tensor cores (DDQST_PRECISION_BF16; RQC model variant): the same step with every GEMM of the
+ * forward, data-gradient and weight-gradient passes on tcgen05 (bf16 operands, fp32 accumulation in TMEM, 3-D TMA
+ * operands; the stored [out,in] weights serve the backward pass as MN-major operands).  params_bf16 is a bf16 copy of
+ * the flat parameter buffer at the same element offsets (ddqst_cast_bf16 once, then kept current by
+ * ddqst_adam_step_dev).  workspace: ddqst_workspace_bytes(DDQST_OP_TRAIN, d, batch, DDQST_PRECISION_BF16). */
+int ddqst_cast_bf16(const float* src, uint16_t* dst_bf16, int64_t n, void* stream);
+int ddqst_train_forward_backward_tc(const ddqst_dims* d, const float* params, const uint16_t* params_bf16,
+                                    const uint16_t* xt_packed, const uint16_t* x0_packed, const int32_t* t,
+                                    const int32_t* basis, int64_t batch, float loss_scale, float* grads, float* loss_out,
+                                    void* workspace, int64_t ws_bytes, void* stream);
+/* Adam / AdamW with the 0-based count of completed steps in device memory (step_dev[0], incremented by the call) and an
+ * optional bf16 shadow of the updated parameters (params_bf16 nullable): nothing in the call depends on host state, so it
+ * can be replayed from a CUDA graph. */
+int ddqst_adam_step_dev(float* params, uint16_t* params_bf16, const float* grads, float* exp_avg, float* exp_avg_sq,
+                        int64_t n, int64_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
+                        int decoupled, float grad_scale, void* stream);
+
 /* ---- M5 + the notebook DDM (single-qubit phase, config C1): SimpleMLP (NB c6:65-102: embed 32, hidden 128,
  * num_hidden 2) and UpgradedMLP (NB c12:58-94: embed 128, hidden 256, num_hidden 3): cat[x, t_emb, b_emb] -> Linear/ReLU
  * stack -> logits[B,2].  Flat parameters in state_dict order: time_emb.weight, basis_emb.weight, then
@@ -207,6 +230,10 @@ int ddqst_selftest_umma(const float* a /* [M,K] fp32 */, const uint16_t* w_bf16 
 /* the same through one cta_group::2 MMA: M = 256*m_pairs rows, n <= 256, CTA pair shares the B operand */
 int ddqst_selftest_umma2(const float* a, const uint16_t* w_bf16, int32_t m_pairs, int32_t n, int32_t k, float* c,
                          void* stream);
+/* the training GEMM kernel alone: C[batch][m,n] fp32 = A . B^T over bf16 operands stored either way round
+ * (a_mn == 0: A is [m,k] row-major, else [k,m]; b_mn == 0: B is [n,k] row-major, else [k,n]); n % 4 == 0 */
+int ddqst_selftest_gemm_tc(const uint16_t* a, const uint16_t* b, int a_mn, int b_mn, int32_t m, int32_t n, int32_t k,
+                           int32_t batch, float* c, void* stream);
 /* synchronises the device; returns the first pipeline-timeout code a tcgen05 kernel recorded (0 = none) */
 int ddqst_debug_tc_status(void);
 
