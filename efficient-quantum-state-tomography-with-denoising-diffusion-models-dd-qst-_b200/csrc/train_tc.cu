@@ -17,6 +17,7 @@
 // GEMM kernel: one 128 x BN output tile per CTA, BK = 64, 4-stage TMA ring, warp 4 = TMA producer, warp 5 = MMA
 // issuer + TMEM allocator, warps 0-3 = epilogue (thread = output row, tcgen05.ld 32x32b).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "sampler_tc.cuh"
 #include "simt.cuh"
@@ -25,7 +26,7 @@
 namespace ddqst {
 
 constexpr int kGtThreads = 192;
-constexpr int kGtStages = 4;
+template <int BN> __host__ __device__ constexpr int gt_stages() { return BN <= 64 ? 8 : 6; }
 constexpr int kGtMaxZ = 32;
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
@@ -77,12 +78,13 @@ struct TcGemm {
   int64_t out_zoff[kGtMaxZ];
   int nq, E, flag;     // qubits (TE_HEAD), embed dim (TE_DCOND), variant flag (TE_W2: 1 = FiLM next, TE_BW1: 1 = l > 0)
   float scale;         // TE_HEAD: loss_scale / (B*N)
+  long long* dbg;      // optional [8] clock64 stamps of CTA (0,0,0) (self test only)
 };
 
 template <int BN>
 __host__ __device__ constexpr int gt_stage_bytes() { return 16384 + BN * 128; }
 template <int BN>
-__host__ __device__ constexpr int gt_smem_bytes() { return 1024 + kGtStages * gt_stage_bytes<BN>() + 256; }
+__host__ __device__ constexpr int gt_smem_bytes() { return 1024 + gt_stages<BN>() * gt_stage_bytes<BN>() + 256; }
 
 __device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 __device__ __forceinline__ float dsilu_fast(float v) { float s = sigmoid_fast(v); return s * (1.0f + v * (1.0f - s)); }
@@ -109,6 +111,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(kGtThreads)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcGemm G) {
   constexpr int STAGE = gt_stage_bytes<BN>();
+  constexpr int kGtStages = gt_stages<BN>();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + kGtStages * STAGE);
@@ -119,6 +122,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN, z = blockIdx.z;
   const int KB = (G.K + 63) >> 6;
 
+  // programmatic dependent launch: let the next kernel of the stream start its prologue now; our own inputs are
+  // only touched after griddepcontrol.wait below (= the previous kernel has completed and flushed)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const bool dbg = G.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (dbg && tid == 0) G.dbg[0] = clock64();
   if (tid == 0) {
     for (int i = 0; i < kGtStages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     mbar_init(bar_acc, 1);
@@ -128,38 +136,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp == 4 && elect_one()) { tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *((volatile uint32_t*)tmem_slot);
+  if (dbg && tid == 0) G.dbg[1] = clock64();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (dbg && tid == 0) G.dbg[2] = clock64();
 
   if (warp == 4) {
     // =============================== TMA producer ===============================
     const uint32_t elected = elect_one();
-    if (elected) { tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); }
     for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % kGtStages;
       const uint32_t ph = (uint32_t)(kb / kGtStages) & 1u;
       mbar_wait(bar_empty + 8 * s, ph ^ 1u, 40);
-      if (elected) {
+      {
+        // coordinates are computed by the whole (converged) warp so they stay in uniform registers; only the
+        // issue itself is predicated on the elected lane (a divergent block makes ptxas wrap every uniform-datapath
+        // instruction in an ELECT / BRA.U.ANY loop)
         const uint32_t full = bar_full + 8 * s;
         const uint32_t dstA = smem_u32(smem + s * STAGE), dstB = dstA + 16384;
-        mbar_expect_tx(full, (uint32_t)STAGE);
         const int kg = kb * 64;
         int ka = kg, za = z * G.a.zmul, kbb = kg, zb = z * G.b.zmul;
         if (G.a.kmod > 0) { za += kg / G.a.kmod; ka = kg % G.a.kmod; }
         if (G.b.kmod > 0) { zb += kg / G.b.kmod; kbb = kg % G.b.kmod; }
+        if (elected) mbar_expect_tx(full, (uint32_t)STAGE);
         if (G.a.mn_major) {
-          tma_load_3d(dstA, &mapA, full, m0, ka, za);
-          tma_load_3d(dstA + 8192, &mapA, full, m0 + 64, ka, za);
+          if (elected) tma_load_3d(dstA, &mapA, full, m0, ka, za);
+          if (elected) tma_load_3d(dstA + 8192, &mapA, full, m0 + 64, ka, za);
         } else {
-          tma_load_3d(dstA, &mapA, full, ka, m0, za);
+          if (elected) tma_load_3d(dstA, &mapA, full, ka, m0, za);
         }
         if (G.b.mn_major) {
 #pragma unroll
-          for (int g = 0; g < BN / 64; ++g) tma_load_3d(dstB + g * 8192, &mapB, full, n0 + g * 64, kbb, zb);
+          for (int g = 0; g < BN / 64; ++g)
+            if (elected) tma_load_3d(dstB + g * 8192, &mapB, full, n0 + g * 64, kbb, zb);
         } else {
-          tma_load_3d(dstB, &mapB, full, kbb, n0, zb);
+          if (elected) tma_load_3d(dstB, &mapB, full, kbb, n0, zb);
         }
       }
       __syncwarp();
@@ -174,15 +189,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t ph = (uint32_t)(kb / kGtStages) & 1u;
       mbar_wait(bar_full + 8 * s, ph, 41);
       tc_fence_after();
-      if (elected) {
+      if (dbg && kb == 0 && elected) G.dbg[3] = clock64();
+      if (dbg && kb == KB - 1 && elected) G.dbg[4] = clock64();
+      {
         const uint32_t aaddr = smem_u32(smem + s * STAGE), baddr = aaddr + 16384;
         const uint64_t ad = G.a.mn_major ? umma_desc_mn_sw128(aaddr, 8192) : umma_desc_sw128(aaddr);
         const uint64_t bd = G.b.mn_major ? umma_desc_mn_sw128(baddr, 8192) : umma_desc_sw128(baddr);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          umma_bf16(tmem_base, desc_adv(ad, j * a_step), desc_adv(bd, j * b_step), idesc, (uint32_t)((kb | j) != 0));
-        umma_commit(bar_empty + 8 * s);
-        if (kb == KB - 1) umma_commit(bar_acc);
+          if (elected) umma_bf16(tmem_base, desc_adv(ad, j * a_step), desc_adv(bd, j * b_step), idesc, (uint32_t)((kb | j) != 0));
+        if (elected) umma_commit(bar_empty + 8 * s);
+        if (elected && kb == KB - 1) umma_commit(bar_acc);
       }
       __syncwarp();
     }
@@ -192,6 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const bool rv = r < G.M;
     mbar_wait(bar_acc, 0, 42);
     tc_fence_after();
+    if (dbg && tid == 0) G.dbg[5] = clock64();
     float loss_acc = 0.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -331,11 +349,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (tid == 0) G.o1[blockIdx.x] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
     }
   }
+  if (dbg && tid == 0) G.dbg[6] = clock64();
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
   }
+  if (dbg && tid == 160) G.dbg[7] = clock64();
 }
 
 // ------------------------------------------------------------------------------------ small CUDA-core kernels
@@ -409,30 +429,58 @@ __global__ void xemb_grad_kernel(int N, int E, int H, const float* __restrict__ 
 
 // torch Adam / AdamW arithmetic (same as train.cu's adam_kernel) with the step count read from device memory (so
 // the whole training step can be replayed from a CUDA graph) and a bf16 shadow of the updated parameters.
-__global__ void adam_tc_kernel(float* __restrict__ p, __nv_bfloat16* __restrict__ shadow, const float* __restrict__ g,
-                               float* __restrict__ m, float* __restrict__ v, int64_t n, const int64_t* __restrict__ step_dev,
-                               float lr, float b1, float b2, float eps, float wd, int decoupled, float gscale) {
+// step_dev[0] = completed steps, step_dev[1] = block-arrival counter: the last block to finish bumps the step.
+// 4 elements per thread (n4 = n / 4 vectors, the flat buffer is 16-byte aligned); the tail runs scalar.
+__device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v, float lr, float b1, float b2, float eps,
+                                          float wd, int decoupled, float gscale, float bc1, float bc2_sqrt) {
+  float grad = g * gscale, param = p;
+  if (decoupled) param *= (1.0f - lr * wd);            // torch AdamW: param.mul_(1 - lr*wd)
+  else if (wd != 0.f) grad += wd * param;              // torch Adam: grad.add(param, alpha=wd)
+  float mi = m + (grad - m) * (1.0f - b1);             // exp_avg.lerp_(grad, 1-beta1)
+  float vi = v * b2 + (1.0f - b2) * grad * grad;       // exp_avg_sq.mul_(b2).addcmul_(grad, grad, 1-b2)
+  m = mi; v = vi;
+  float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p = param - (lr / bc1) * (mi / denom);
+  return p;
+}
+__global__ void __launch_bounds__(256)
+adam_tc_kernel(float* __restrict__ p, __nv_bfloat16* __restrict__ shadow, const float* __restrict__ g,
+               float* __restrict__ m, float* __restrict__ v, int64_t n, int64_t* __restrict__ step_dev,
+               float lr, float b1, float b2, float eps, float wd, int decoupled, float gscale) {
   __shared__ float s_bc1, s_bc2s;
   if (threadIdx.x == 0) {
-    const double st = (double)(step_dev[0] + 1);
+    const double st = (double)(*((volatile int64_t*)step_dev) + 1);
     s_bc1 = (float)(1.0 - pow((double)b1, st));
     s_bc2s = (float)sqrt(1.0 - pow((double)b2, st));
   }
   __syncthreads();
   const float bc1 = s_bc1, bc2_sqrt = s_bc2s;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float grad = g[i] * gscale, param = p[i];
-  if (decoupled) param *= (1.0f - lr * wd);
-  else if (wd != 0.f) grad += wd * param;
-  float mi = m[i] + (grad - m[i]) * (1.0f - b1);
-  float vi = v[i] * b2 + (1.0f - b2) * grad * grad;
-  m[i] = mi; v[i] = vi;
-  float denom = sqrtf(vi) / bc2_sqrt + eps;
-  param = param - (lr / bc1) * (mi / denom);
-  p[i] = param;
-  if (shadow) shadow[i] = __float2bfloat16(param);
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    adam_one(pp.x, gg.x, mm.x, vv.x, lr, b1, b2, eps, wd, decoupled, gscale, bc1, bc2_sqrt);
+    adam_one(pp.y, gg.y, mm.y, vv.y, lr, b1, b2, eps, wd, decoupled, gscale, bc1, bc2_sqrt);
+    adam_one(pp.z, gg.z, mm.z, vv.z, lr, b1, b2, eps, wd, decoupled, gscale, bc1, bc2_sqrt);
+    adam_one(pp.w, gg.w, mm.w, vv.w, lr, b1, b2, eps, wd, decoupled, gscale, bc1, bc2_sqrt);
+    reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+    if (shadow) reinterpret_cast<uint2*>(shadow)[i] = make_uint2(pack_bf16(pp.x, pp.y), pack_bf16(pp.z, pp.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    float pv = p[i], mv = m[i], vv = v[i];
+    adam_one(pv, g[i], mv, vv, lr, b1, b2, eps, wd, decoupled, gscale, bc1, bc2_sqrt);
+    p[i] = pv; m[i] = mv; v[i] = vv;
+    if (shadow) shadow[i] = __float2bfloat16(pv);
+  }
+  __syncthreads();                      // every thread of this block has read the step (through s_bc*) long ago
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long arrived = atomicAdd((unsigned long long*)(step_dev + 1), 1ull);
+    if (arrived == (unsigned long long)gridDim.x - 1ull) { step_dev[1] = 0; step_dev[0] += 1; }
+  }
 }
+
 __global__ void step_inc_kernel(int64_t* step_dev) { if (threadIdx.x == 0 && blockIdx.x == 0) step_dev[0] += 1; }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
@@ -468,6 +516,13 @@ struct HostOperand {
 static HostOperand op_k(const void* base, int64_t mn, int64_t k, int64_t ld) { return HostOperand{base, 0, mn, k, 1, ld, mn * ld, 0, 0}; }
 static HostOperand op_mn(const void* base, int64_t mn, int64_t k, int64_t ld) { return HostOperand{base, 1, mn, k, 1, ld, k * ld, 0, 0}; }
 
+// DDQST_TC_PDL=0 launches the GEMMs fully serialised (debugging aid)
+static bool tc_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DDQST_TC_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 template <int BN, int EPI>
 static int launch_gemm_bn(const HostOperand& A, const HostOperand& B, TcGemm g, int zcount, cudaStream_t s) {
   CUtensorMap ma, mb;
@@ -482,9 +537,17 @@ static int launch_gemm_bn(const HostOperand& A, const HostOperand& B, TcGemm g, 
     DDQST_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes<BN>()));
     attr_set = true;
   }
-  dim3 grid((unsigned)((g.M + 127) / 128), (unsigned)((g.N + BN - 1) / BN), (unsigned)zcount);
-  gemm_tc_kernel<BN, EPI><<<grid, kGtThreads, gt_smem_bytes<BN>(), s>>>(ma, mb, g);
-  DDQST_LAUNCH_OK();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((g.M + 127) / 128), (unsigned)((g.N + BN - 1) / BN), (unsigned)zcount);
+  cfg.blockDim = dim3(kGtThreads);
+  cfg.dynamicSmemBytes = gt_smem_bytes<BN>();
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tc_pdl_enabled() ? 1 : 0;
+  DDQST_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI>, ma, mb, g));
   return DDQST_OK;
 }
 
@@ -628,12 +691,13 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
       DDQST_TRY(launch_gemm<TE_BW1>(op_k(dz + 2 * l * BH, B, H, H), op_mn(shadow + pr.w1[l], H, H, H), g, 1, s));
     }
   }
-  {  // dcond = sum_l dgb_l . Wfilm_l, scattered into the time / basis embedding gradients
-    TcGemm g = base_gemm((int)B, 2 * E, L * 2 * H);
+  {  // dcond = sum_l dgb_l . Wfilm_l, scattered into the time / basis embedding gradients; the sum over blocks is a
+     // split-K over z (one block per z): the epilogue accumulates with atomics anyway
+    TcGemm g = base_gemm((int)B, 2 * E, 2 * H);
     g.o0 = grads + pr.time_emb; g.o1 = grads + pr.basis_emb; g.i0 = t; g.i1 = basis;
-    HostOperand A{dgb, 0, B, 2 * H, L, 2 * H, BG, 2 * H, 0};
-    HostOperand Bo{shadow + pr.film_w[0], 1, 2 * E, 2 * H, L, 2 * E, blk_stride > 0 ? blk_stride : (int64_t)2 * H * 2 * E, 2 * H, 0};
-    DDQST_TRY(launch_gemm<TE_DCOND>(A, Bo, g, 1, s));
+    HostOperand A{dgb, 0, B, 2 * H, L, 2 * H, BG, 0, 1};
+    HostOperand Bo{shadow + pr.film_w[0], 1, 2 * E, 2 * H, L, 2 * E, blk_stride > 0 ? blk_stride : (int64_t)2 * H * 2 * E, 0, 1};
+    DDQST_TRY(launch_gemm<TE_DCOND>(A, Bo, g, L, s));
   }
   // ------------------------------------------------------------------ backward: weight gradients (dY^T . X over the batch)
   {  // W1_l, W2_l for every block: z = 2l (dz1_l, a_l), 2l+1 (dz2_l, u_l)
@@ -721,24 +785,35 @@ int ddqst_adam_step_dev(float* params, uint16_t* params_bf16, const float* grads
   DDQST_REQUIRE(n >= 0 && step_dev, DDQST_EINVAL_SHAPE, "n=%lld", (long long)n);
   if (n > 0) {
     DDQST_REQUIRE(params && grads && exp_avg && exp_avg_sq, DDQST_EINVAL_SHAPE, "NULL argument");
-    adam_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, (__nv_bfloat16*)params_bf16, grads, exp_avg,
-                                                                                 exp_avg_sq, n, step_dev, lr, beta1, beta2, eps,
-                                                                                 weight_decay, decoupled, grad_scale);
+    int64_t blocks = ((n >> 2) + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    adam_tc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(params, (__nv_bfloat16*)params_bf16, grads, exp_avg, exp_avg_sq,
+                                                                      n, step_dev, lr, beta1, beta2, eps, weight_decay, decoupled,
+                                                                      grad_scale);
+    DDQST_LAUNCH_OK();
+  } else {
+    step_inc_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_dev);
     DDQST_LAUNCH_OK();
   }
-  step_inc_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_dev);
-  DDQST_LAUNCH_OK();
   return DDQST_OK;
 }
 
 // C[z][M,N] fp32 = A . B^T over bf16 operands given in either storage order (self test of the training GEMM kernel):
 // a_mn == 0: A is [M,K] row-major, else [K,M]; b_mn == 0: B is [N,K] row-major, else [K,N].
+int ddqst_selftest_gemm_tc_dbg(const uint16_t* a, const uint16_t* b, int a_mn, int b_mn, int32_t m, int32_t n, int32_t k,
+                               int32_t batch, float* c, long long* dbg, void* stream);
 int ddqst_selftest_gemm_tc(const uint16_t* a, const uint16_t* b, int a_mn, int b_mn, int32_t m, int32_t n, int32_t k,
                            int32_t batch, float* c, void* stream) {
+  return ddqst_selftest_gemm_tc_dbg(a, b, a_mn, b_mn, m, n, k, batch, c, nullptr, stream);
+}
+int ddqst_selftest_gemm_tc_dbg(const uint16_t* a, const uint16_t* b, int a_mn, int b_mn, int32_t m, int32_t n, int32_t k,
+                               int32_t batch, float* c, long long* dbg, void* stream) {
   DDQST_TRY(check_arch());
   DDQST_REQUIRE(m >= 1 && n >= 4 && n % 4 == 0 && k >= 1 && batch >= 1 && batch <= kGtMaxZ, DDQST_EINVAL_SHAPE, "selftest shape");
   TcGemm g{};
-  g.M = m; g.N = n; g.K = k; g.o0 = c; g.ld = n;
+  g.M = m; g.N = n; g.K = k; g.o0 = c; g.ld = n; g.dbg = dbg;
   for (int z = 0; z < batch; ++z) g.out_zoff[z] = (int64_t)z * m * n;
   HostOperand A = a_mn ? HostOperand{a, 1, m, k, batch, m, (int64_t)k * m, 0, 1} : HostOperand{a, 0, m, k, batch, k, (int64_t)m * k, 0, 1};
   HostOperand B = b_mn ? HostOperand{b, 1, n, k, batch, n, (int64_t)k * n, 0, 1} : HostOperand{b, 0, n, k, batch, k, (int64_t)n * k, 0, 1};

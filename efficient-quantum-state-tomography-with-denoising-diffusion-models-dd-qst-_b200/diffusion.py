@@ -62,10 +62,10 @@ class NativeAdam:
 
     @property
     def step_dev(self) -> torch.Tensor:
-        """Count of completed steps in device memory (int64[1]); read by the graph-replayable kernels."""
+        """int64[2] in device memory: [0] = count of completed steps (read by the graph-replayable kernels), [1] = scratch."""
         p = self.model.flat_params
         if self._step_dev is None or self._step_dev.device != p.device:
-            self._step_dev = torch.full((1,), self.step_count, dtype=torch.int64, device=p.device)
+            self._step_dev = torch.tensor([self.step_count, 0], dtype=torch.int64, device=p.device)
         return self._step_dev
 
     def step_device(self, grads: torch.Tensor, grad_scale: float = 1.0, shadow: torch.Tensor | None = None):

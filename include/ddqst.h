@@ -183,8 +183,8 @@ int ddqst_train_forward_backward_tc(const ddqst_dims* d, const float* params, co
                                     const uint16_t* xt_packed, const uint16_t* x0_packed, const int32_t* t,
                                     const int32_t* basis, int64_t batch, float loss_scale, float* grads, float* loss_out,
                                     void* workspace, int64_t ws_bytes, void* stream);
-/* Adam / AdamW with the 0-based count of completed steps in device memory (step_dev[0], incremented by the call) and an
- * optional bf16 shadow of the updated parameters (params_bf16 nullable): nothing in the call depends on host state, so it
+/* Adam / AdamW with the count of completed steps in device memory (step_dev: int64[2], [0] = completed steps, incremented
+ * by the call, [1] = scratch that must start at 0) and an optional bf16 shadow of the updated parameters (params_bf16 nullable): nothing in the call depends on host state, so it
  * can be replayed from a CUDA graph. */
 int ddqst_adam_step_dev(float* params, uint16_t* params_bf16, const float* grads, float* exp_avg, float* exp_avg_sq,
                         int64_t n, int64_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay,

@@ -149,6 +149,6 @@ def test_train_graph_replay_matches_eager(dq):
     assert dq._lib.load().ddqst_debug_tc_status() == 0
     # the embedding scatter uses fp32 atomics, so runs agree to rounding, not bitwise
     assert np.allclose(eager[1:], replay, rtol=2e-3, atol=2e-4), (eager, replay)
-    assert int(og.step_dev.item()) == 4 and og.step_count == 4
+    assert int(og.step_dev[0].item()) == 4 and og.step_count == 4
     rel = (me.flat_params - mg.flat_params).norm().item() / me.flat_params.norm().item()
     assert rel < 1e-3, rel
