@@ -308,9 +308,10 @@ struct JacobiCtl {
   int sweeps_done;
 };
 
-__global__ void jacobi_init_kernel(const double2* __restrict__ A, int n, double2* __restrict__ GT, double2* __restrict__ VT,
-                                   JacobiCtl* ctl) {
-  // single block: Frobenius norm -> sigma, then GT = conj(A) + sigma I, VT = I
+__global__ void jacobi_init_kernel(const double2* __restrict__ A, int n, double2* __restrict__ GT, JacobiCtl* ctl) {
+  // single block: Frobenius norm -> sigma, then GT = columns of A + sigma I.  The eigenvector matrix is never
+  // accumulated: at convergence G = A'V has orthogonal columns lambda'_j v_j with lambda'_j >= sigma/2 > 0, so
+  // v_j = g_j / ||g_j|| (jacobi_evals_kernel) -- half the rotation work and memory traffic of tracking V.
   __shared__ double scratch[96];
   double f = 0.0, z1 = 0.0, z2 = 0.0;
   const int64_t total = (int64_t)n * n;
@@ -330,11 +331,10 @@ __global__ void jacobi_init_kernel(const double2* __restrict__ A, int n, double2
     v.x = 0.5 * (v.x + w.x); v.y = 0.5 * (v.y - w.y);
     if (i == j) { v.x += sigma; v.y = 0.0; }
     GT[e] = v;
-    VT[e] = make_double2(i == j ? 1.0 : 0.0, 0.0);
   }
 }
 
-__global__ void __launch_bounds__(256) jacobi_sweeps_kernel(double2* __restrict__ GT, double2* __restrict__ VT, int n,
+__global__ void __launch_bounds__(256) jacobi_sweeps_kernel(double2* __restrict__ GT, int n,
                                                             int max_sweeps, double tol, JacobiCtl* ctl) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double scratch[96];
@@ -366,17 +366,11 @@ __global__ void __launch_bounds__(256) jacobi_sweeps_kernel(double2* __restrict_
           double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
           double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
           double pr = gr / gabs, pi = -gi / gabs;   // e^{-i phi} = conj(gamma)/|gamma|
-          double2* vp = VT + (int64_t)p * n;
-          double2* vq = VT + (int64_t)q * n;
           for (int i = tid; i < n; i += blockDim.x) {
             double2 x = gp[i], y = gq[i];
             double2 yr = make_double2(y.x * pr - y.y * pi, y.x * pi + y.y * pr);
             gp[i] = make_double2(c * x.x - s * yr.x, c * x.y - s * yr.y);
             gq[i] = make_double2(s * x.x + c * yr.x, s * x.y + c * yr.y);
-            x = vp[i]; y = vq[i];
-            yr = make_double2(y.x * pr - y.y * pi, y.x * pi + y.y * pr);
-            vp[i] = make_double2(c * x.x - s * yr.x, c * x.y - s * yr.y);
-            vq[i] = make_double2(s * x.x + c * yr.x, s * x.y + c * yr.y);
           }
           if (tid == 0) atomicAdd(&ctl->rotations[sweep], 1);
         }
@@ -390,14 +384,93 @@ __global__ void __launch_bounds__(256) jacobi_sweeps_kernel(double2* __restrict_
   }
 }
 
-// evals[j] = ||G[:,j]|| - sigma
-__global__ void jacobi_evals_kernel(const double2* __restrict__ GT, int n, const JacobiCtl* ctl, double* __restrict__ evals) {
+// evals[j] = ||G[:,j]|| - sigma ; eigenvector j = G[:,j] / ||G[:,j]||  (rows of VT)
+__global__ void jacobi_evals_kernel(const double2* __restrict__ GT, int n, const JacobiCtl* ctl, double* __restrict__ evals,
+                                    double2* __restrict__ VT) {
   __shared__ double scratch[96];
   int j = blockIdx.x;
   double a = 0.0, z1 = 0.0, z2 = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) { double2 v = GT[(int64_t)j * n + i]; a += v.x * v.x + v.y * v.y; }
   block_sum3(a, z1, z2, scratch);
-  if (threadIdx.x == 0) evals[j] = sqrt(a) - ctl->sigma;
+  const double nrm = sqrt(a), inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+  if (threadIdx.x == 0) evals[j] = nrm - ctl->sigma;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double2 v = GT[(int64_t)j * n + i];
+    VT[(int64_t)j * n + i] = make_double2(v.x * inv, v.y * inv);
+  }
+}
+
+// The same sweeps for n <= 256 inside ONE thread-block cluster: one warp per column pair (columns stay in L2, each
+// lane keeps its n/32 elements of both columns in registers between the dot products and the rotation), and the
+// step barrier is the hardware cluster barrier instead of a cooperative grid sync (the solver is barrier-bound:
+// (n-1) dependent steps per sweep, ~9 sweeps).
+constexpr int kJcThreads = 256;
+__device__ __forceinline__ void jc_cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int EPL>
+__global__ void __launch_bounds__(kJcThreads) jacobi_cluster_kernel(double2* __restrict__ GT, int n, int max_sweeps, double tol,
+                                                                   JacobiCtl* ctl) {
+  const int lane = threadIdx.x & 31;
+  uint32_t crank, csize;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+  const int wpc = kJcThreads / 32;
+  const int gwarp = (int)crank * wpc + (threadIdx.x >> 5), nwarps = (int)csize * wpc;
+  const int m = n - 1, npairs = n / 2;
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    int rot = 0;
+    for (int step = 0; step < m; ++step) {
+      for (int pair = gwarp; pair < npairs; pair += nwarps) {
+        int p, q;
+        if (pair == 0) { p = m; q = step % m; }
+        else { p = (step + pair) % m; q = (step + m - pair) % m; }
+        if (p > q) { int tmp = p; p = q; q = tmp; }
+        double2* gp = GT + (int64_t)p * n;
+        double2* gq = GT + (int64_t)q * n;
+        double2 x[EPL], y[EPL];
+        double a = 0.0, b = 0.0, gr = 0.0, gi = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          const int i = lane + 32 * e;
+          if (i < n) { x[e] = __ldcg(gp + i); y[e] = __ldcg(gq + i); }
+          else { x[e] = make_double2(0.0, 0.0); y[e] = make_double2(0.0, 0.0); }
+          a += x[e].x * x[e].x + x[e].y * x[e].y;
+          b += y[e].x * y[e].x + y[e].y * y[e].y;
+          gr += x[e].x * y[e].x + x[e].y * y[e].y;     // conj(x)*y
+          gi += x[e].x * y[e].y - x[e].y * y[e].x;
+        }
+        a = warp_sum(a); b = warp_sum(b); gr = warp_sum(gr); gi = warp_sum(gi);
+        // lanes summed in different orders: take lane 0's values so the whole warp takes the same branch and angle
+        a = __shfl_sync(0xFFFFFFFFu, a, 0); b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        gr = __shfl_sync(0xFFFFFFFFu, gr, 0); gi = __shfl_sync(0xFFFFFFFFu, gi, 0);
+        const double gabs = sqrt(gr * gr + gi * gi);
+        if (gabs > tol * sqrt(a * b) && gabs > 0.0) {
+          const double zeta = (b - a) / (2.0 * gabs);
+          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+          const double pr = gr / gabs, pi = -gi / gabs;   // e^{-i phi} = conj(gamma)/|gamma|
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) {
+            const int i = lane + 32 * e;
+            if (i < n) {
+              const double2 yr = make_double2(y[e].x * pr - y[e].y * pi, y[e].x * pi + y[e].y * pr);
+              __stcg(gp + i, make_double2(c * x[e].x - s * yr.x, c * x[e].y - s * yr.y));
+              __stcg(gq + i, make_double2(s * x[e].x + c * yr.x, s * x[e].y + c * yr.y));
+            }
+          }
+          ++rot;
+        }
+      }
+      jc_cluster_barrier();
+    }
+    if (lane == 0 && rot > 0) atomicAdd(&ctl->rotations[sweep], rot);
+    jc_cluster_barrier();
+    const int total = __ldcg(&ctl->rotations[sweep]);
+    if (total == 0) { ++sweep; break; }
+  }
+  if (gwarp == 0 && lane == 0) ctl->sweeps_done = sweep;
 }
 
 // clip negatives, renormalise when the sum is positive (RQC/reconstruct.py:50-52); single block
@@ -510,22 +583,70 @@ __global__ void partial_trace_kernel(const double2* __restrict__ rho, int dim, i
 
 // Hermitian eigendecomposition of A[n,n] (n a power of two >= 2): evals[n], VT (rows = eigenvectors).
 // ws: GT[n*n] double2, then JacobiCtl.
+template <int EPL>
+static int launch_jacobi_cluster(double2* GT, int n, int max_sweeps, double tol, JacobiCtl* ctl, int csize, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DDQST_CUDA_OK(cudaFuncSetAttribute(jacobi_cluster_kernel<EPL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)csize);
+  cfg.blockDim = dim3(kJcThreads);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // a 16-CTA cluster is a non-portable size: if this device / partition cannot co-schedule it, halve until it fits
+  // (the kernel loops over pairs, so any cluster size is correct)
+  for (;;) {
+    int fits = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&fits, jacobi_cluster_kernel<EPL>, &cfg);
+    if (e == cudaSuccess && fits >= 1) break;
+    (void)cudaGetLastError();
+    DDQST_REQUIRE(csize > 1, DDQST_ECUDA, "no thread-block cluster configuration fits for the Jacobi eigensolver");
+    csize /= 2;
+    cfg.gridDim = dim3((unsigned)csize);
+    attr[0].val.clusterDim.x = (unsigned)csize;
+  }
+  DDQST_CUDA_OK(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<EPL>, GT, n, max_sweeps, tol, ctl));
+  return DDQST_OK;
+}
+
+// Hermitian eigendecomposition of A[n,n] (n a power of two >= 2): evals[n], VT (rows = eigenvectors).
+// ws: GT[n*n] double2, then JacobiCtl.
 static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char* ws, cudaStream_t s) {
   double2* GT = (double2*)ws;
   JacobiCtl* ctl = (JacobiCtl*)(ws + (int64_t)16 * n * n);
-  jacobi_init_kernel<<<1, 1024, 0, s>>>(A, n, GT, VT, ctl);
+  jacobi_init_kernel<<<1, 1024, 0, s>>>(A, n, GT, ctl);
   DDQST_LAUNCH_OK();
-  int per_sm = 0;
-  DDQST_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_sweeps_kernel, 256, 0));
-  int grid = n / 2;
-  int cap = per_sm * num_sms();
-  if (grid > cap) grid = cap;
-  if (grid < 1) grid = 1;
   int max_sweeps = 60;
   double tol = 1e-15;
-  void* args[] = {&GT, &VT, &n, &max_sweeps, &tol, &ctl};
-  DDQST_CUDA_OK(cudaLaunchCooperativeKernel((void*)jacobi_sweeps_kernel, dim3(grid), dim3(256), args, 0, s));
-  jacobi_evals_kernel<<<n, 128, 0, s>>>(GT, n, ctl, evals);
+  if (n <= 256) {
+    // one warp per column pair, 8 warps per CTA, up to 16 CTAs in the cluster
+    int csize = (n / 2 + kJcThreads / 32 - 1) / (kJcThreads / 32);
+    if (csize < 1) csize = 1;
+    if (csize > 16) csize = 16;
+    const int epl = n <= 32 ? 1 : n / 32;
+    switch (epl) {
+      case 1: DDQST_TRY(launch_jacobi_cluster<1>(GT, n, max_sweeps, tol, ctl, csize, s)); break;
+      case 2: DDQST_TRY(launch_jacobi_cluster<2>(GT, n, max_sweeps, tol, ctl, csize, s)); break;
+      case 4: DDQST_TRY(launch_jacobi_cluster<4>(GT, n, max_sweeps, tol, ctl, csize, s)); break;
+      default: DDQST_TRY(launch_jacobi_cluster<8>(GT, n, max_sweeps, tol, ctl, csize, s)); break;
+    }
+  } else {
+    int per_sm = 0;
+    DDQST_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_sweeps_kernel, 256, 0));
+    int grid = n / 2;
+    int cap = per_sm * num_sms();
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    void* args[] = {&GT, &n, &max_sweeps, &tol, &ctl};
+    DDQST_CUDA_OK(cudaLaunchCooperativeKernel((void*)jacobi_sweeps_kernel, dim3(grid), dim3(256), args, 0, s));
+  }
+  jacobi_evals_kernel<<<n, 128, 0, s>>>(GT, n, ctl, evals, VT);
   DDQST_LAUNCH_OK();
   return DDQST_OK;
 }

@@ -296,12 +296,30 @@ def test_train_steps_match_reference(dq, tag):
     diff = dq.DiscreteDiffusion(m, T, "cuda", schedule="cosine" if tag == "B" else "linear", seed=int(z["train_seed"][0]))
     opt = dq.NativeAdam(m, lr=1e-3) if tag == "B" else dq.NativeAdam(m, lr=1e-4, weight_decay=0.01, decoupled=True)
     x0, b0 = torch.from_numpy(z["train_x0"]).cuda(), torch.from_numpy(z["train_basis"]).cuda()
-    losses = [diff.train_step(x0, b0, opt).item() for _ in range(3)]
+    losses = [diff.train_step(x0, b0, opt, precision="fp32").item() for _ in range(3)]      # exact (CUDA-core fp32) mode
     assert np.allclose(losses, z["train_losses"], atol=1e-5), (losses, z["train_losses"])
     want = golden_state_dict(z, "trained.")
     got = m.state_dict()
     for k, v in want.items():
         assert torch.allclose(got[k].cpu(), v, atol=1e-5), k
+
+
+def test_train_steps_tensor_core_track_reference(dq):
+    """The default (tcgen05 bf16) training step on the reference fixture: losses within the 1e-2 bar north_star sets for
+    bf16 denoiser arithmetic, weights within 1e-3 absolute of the reference's after 3 Adam steps (lr 1e-3)."""
+    z = load_golden("model_B_small.npz")
+    m, (N, NB, T, *_r) = make_model(dq, z, "B")
+    diff = dq.DiscreteDiffusion(m, T, "cuda", schedule="cosine", seed=int(z["train_seed"][0]))
+    assert diff.train_precision() == "bf16"
+    opt = dq.NativeAdam(m, lr=1e-3)
+    x0, b0 = torch.from_numpy(z["train_x0"]).cuda(), torch.from_numpy(z["train_basis"]).cuda()
+    losses = [diff.train_step(x0, b0, opt).item() for _ in range(3)]
+    assert dq._lib.load().ddqst_debug_tc_status() == 0
+    assert np.allclose(losses, z["train_losses"], rtol=1e-2), (losses, z["train_losses"])
+    want = golden_state_dict(z, "trained.")
+    got = m.state_dict()
+    for k, v in want.items():
+        assert (got[k].cpu() - v).abs().max().item() < 2.5e-3, k      # Adam moves each weight by <= lr per step
 
 
 def test_autograd_surface_matches_oracle_gradients(dq):
