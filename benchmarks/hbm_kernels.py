@@ -36,6 +36,7 @@ def timed(fn, iters=10, warmup=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
+    ap.add_argument("--only-hist", action="store_true")
     args = ap.parse_args()
     lib = dq._lib.load()
     P, S = dq._lib.ptr, dq._lib.stream_ptr
@@ -69,6 +70,8 @@ def main():
     ms = timed(lambda: dq._lib.check(lib.ddqst_histogram(P(d16), 2, n16, 10, P(h10), S())))
     report("histogram N=10 uniform", 2 * n16 + 4096, ms, "134M shots, uint16")
     del data, peaked, d16
+    if args.only_hist:
+        return
 
     # ---- noising (D2): x0 uint16 in, t drawn in-kernel (int32 out), x_t uint16 out
     B = 1 << 27

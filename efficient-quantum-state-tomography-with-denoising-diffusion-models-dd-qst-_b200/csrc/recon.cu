@@ -33,13 +33,30 @@ __global__ void __launch_bounds__(256) histogram_kernel(const T* __restrict__ da
     bool live = i < nvec;
     if (live) w = __ldg(v4 + i);
     uint32_t words[4] = {w.x, w.y, w.z, w.w};
+    // Skew probe on the first shot of the vector: spread-out data (the common case at N >= 9) goes straight to the
+    // shared-memory atomic unit, one ATOMS per shot; a warp that sees one outcome repeated (GHZ-like peaks) takes the
+    // match_any path, which folds equal keys into one atomic per distinct value.
+    const uint32_t first = live ? ((words[0] & (sizeof(T) == 1 ? 0xFFu : 0xFFFFu)) & mask_bins) : 0xFFFFFFFFu;
+    const uint32_t p0 = __match_any_sync(0xFFFFFFFFu, first);
+    const bool skewed = __any_sync(0xFFFFFFFFu, __popc(p0) > 4);
+    if (!skewed) {
+      if (live) {
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      uint32_t word = words[(k * sizeof(T)) / 4];
-      uint32_t v = (word >> (8 * ((k * sizeof(T)) % 4))) & (sizeof(T) == 1 ? 0xFFu : 0xFFFFu);
-      uint32_t key = live ? (v & mask_bins) : 0xFFFFFFFFu;
-      uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-      if (live && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(bins + key, (uint32_t)__popc(peers));
+        for (int k = 0; k < VEC; ++k) {
+          uint32_t word = words[(k * sizeof(T)) / 4];
+          uint32_t v = (word >> (8 * ((k * sizeof(T)) % 4))) & (sizeof(T) == 1 ? 0xFFu : 0xFFFFu);
+          atomicAdd(bins + (v & mask_bins), 1u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        uint32_t word = words[(k * sizeof(T)) / 4];
+        uint32_t v = (word >> (8 * ((k * sizeof(T)) % 4))) & (sizeof(T) == 1 ? 0xFFu : 0xFFFFu);
+        uint32_t key = live ? (v & mask_bins) : 0xFFFFFFFFu;
+        uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+        if (live && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(bins + key, (uint32_t)__popc(peers));
+      }
     }
   }
   // tail elements (n not a multiple of VEC): first block, plain atomics
@@ -56,9 +73,12 @@ __global__ void __launch_bounds__(256) histogram_kernel(const T* __restrict__ da
 }
 
 // N <= 8 fast path: every thread owns a private set of 256 16-bit counters in shared memory, laid out
-// [bin>>1][lane] so that a warp's 32 read-modify-writes always hit 32 different banks: no atomics and no
-// conflicts in the streaming loop (LDS.U16 / IADD / STS.U16 per shot).  Counters are folded into global
-// memory with one atomicAdd per (warp, bin) at the end (and before a private counter could overflow).
+// [bin>>1][lane] (32-bit words, two bins per word) so that a warp's 32 read-modify-writes always hit 32 different
+// banks: no atomics and no conflicts in the streaming loop (LDS.U16 / IADD / STS.U16 per shot; measured alternatives:
+// a [bin][lane] uint16 layout halves the address arithmetic but pairs lanes on one bank -> 2 wavefronts per access and
+// the same time; reading four counters before writing any adds compare instructions and becomes issue-bound).
+// Counters are folded into global memory with one atomicAdd per (warp, bin) at the end (and before a private
+// counter could overflow).
 template <typename T>
 __global__ void __launch_bounds__(128) histogram_private_kernel(const T* __restrict__ data, int64_t n, int nbins,
                                                                 uint32_t* __restrict__ hist) {
@@ -94,18 +114,44 @@ __global__ void __launch_bounds__(128) histogram_private_kernel(const T* __restr
     __syncwarp();
   };
   int since_fold = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+  auto load16 = [&](int64_t i) {
     uint4 w;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(v4 + i));
+    return w;
+  };
+  auto consume = [&](const uint4& w) {
     uint32_t words[4] = {w.x, w.y, w.z, w.w};
+    if (sizeof(T) == 1) {
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      uint32_t word = words[(k * sizeof(T)) / 4];
-      bump((word >> (8 * ((k * sizeof(T)) % 4))) & (sizeof(T) == 1 ? 0xFFu : 0xFFFFu) & mask_bins);
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t x = words[k];
+        bump(x & mask_bins); bump((x >> 8) & mask_bins); bump((x >> 16) & mask_bins); bump((x >> 24) & mask_bins);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const uint32_t x = words[k]; bump(x & mask_bins); bump((x >> 16) & mask_bins); }
     }
-    if (++since_fold == 65535 / VEC) {                  // a private counter cannot have exceeded 65535 yet
-      // warp-uniform trip counts are not guaranteed at the tail, so only fold when the whole warp is here
-      if (__activemask() == 0xFFFFFFFFu) { fold(); since_fold = 0; }
+  };
+  // four 16-byte loads in flight per thread: the counter updates run under the HBM latency of the next batch
+  constexpr int DEPTH = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint4 buf[DEPTH];
+#pragma unroll
+  for (int d = 0; d < DEPTH; ++d) buf[d] = (i + d * stride < nvec) ? load16(i + d * stride) : make_uint4(0, 0, 0, 0);
+  for (; i < nvec; i += DEPTH * stride) {
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) {
+      const int64_t cur = i + d * stride;
+      if (cur >= nvec) break;
+      const uint4 w = buf[d];
+      const int64_t nxt = cur + DEPTH * stride;
+      if (nxt < nvec) buf[d] = load16(nxt);
+      consume(w);
+      if (++since_fold == 65535 / VEC) {                // a private counter cannot have exceeded 65535 yet
+        // warp-uniform trip counts are not guaranteed at the tail, so only fold when the whole warp is here
+        if (__activemask() == 0xFFFFFFFFu) { fold(); since_fold = 0; }
+      }
     }
   }
   if (blockIdx.x == 0)
