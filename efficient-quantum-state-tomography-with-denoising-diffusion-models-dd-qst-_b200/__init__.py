@@ -7,6 +7,7 @@ plus the batched ``DiscreteDiffusion.sample(bases, n_shots)``, ``train_step`` an
 """
 from . import _lib
 from ._build import build
+from .dataset import QuantumStateDataset, load_circuit_records, state_vector_of
 from .diffusion import DiscreteDiffusion, NativeAdam, TrainGraph, cosine_schedule, linear_schedule
 from .distributed import all_reduce_histograms, sample_sharded, shard_range
 from .model import ConditionalD3PM, pack_bits, unpack_bits
@@ -19,5 +20,5 @@ __all__ = [
     "ConditionalD3PM", "DiscreteDiffusion", "NativeAdam", "TrainGraph", "cosine_schedule", "linear_schedule", "pack_bits", "unpack_bits",
     "DensityMatrix", "Statevector", "basis_strings", "get_coefficient", "get_metrics", "get_pauli_matrix",
     "histogram_samples", "linear_inversion", "linear_inversion_raw", "make_positive_semidefinite", "state_fidelity",
-    "all_reduce_histograms", "sample_sharded", "shard_range", "build",
+    "QuantumStateDataset", "load_circuit_records", "state_vector_of", "all_reduce_histograms", "sample_sharded", "shard_range", "build",
 ]

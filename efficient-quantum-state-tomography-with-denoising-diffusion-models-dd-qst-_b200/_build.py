@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libddqst.so")
-SOURCES = ["api.cu", "simt.cu", "recon.cu", "sampler_tc.cu", "train.cu", "train_tc.cu", "mlp.cu"]
+SOURCES = ["api.cu", "simt.cu", "recon.cu", "sampler_tc.cu", "train.cu", "train_tc.cu", "mlp.cu", "dataset.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

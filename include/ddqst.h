@@ -190,6 +190,20 @@ int ddqst_adam_step_dev(float* params, uint16_t* params_bf16, const float* grads
                         int64_t n, int64_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
                         int decoupled, float grad_scale, void* stream);
 
+/* ---- dataset unrolling (RQC/dataset.py:47-65, SS/dataset.py:14-33; call site RQC/main.py:84-92 DataLoader(shuffle=True)).
+ * hist[n_rows, 2^N] uint32: one row per measurement record, outcome index s = sum_q bit_q << q (= the reference's
+ * reversed counts key).  A shot is addressed by its position in the canonical unrolled order (row-major, outcomes
+ * ascending inside a row).  counts_scan: cum[n_rows, 2^N] = inclusive running counts per row, row_start[n_rows + 1] =
+ * shots before each row (row_start[n_rows] = total).  counts_gather: for j < count, position p = (start + j) % total,
+ * sent through a keyed bijection of [0, total) when permute != 0 (4-round Feistel network + cycle walking, keyed by
+ * (seed, epoch): one epoch of DataLoader(shuffle=True)); outputs (each nullable): packed bitstring, basis index of the
+ * row (row_basis[row], or the row number when row_basis is NULL), and the reference's int64[count, N] bit layout. */
+int ddqst_counts_scan(const uint32_t* hist, int64_t n_rows, int32_t num_qubits, uint32_t* cum, int64_t* row_start,
+                      void* stream);
+int ddqst_counts_gather(const uint32_t* cum, const int64_t* row_start, const int32_t* row_basis, int64_t n_rows,
+                        int32_t num_qubits, int64_t total, int permute, uint64_t seed, uint64_t epoch, int64_t start,
+                        int64_t count, uint16_t* out_x0_packed, int32_t* out_basis, int64_t* out_bits, void* stream);
+
 /* ---- M5 + the notebook DDM (single-qubit phase, config C1): SimpleMLP (NB c6:65-102: embed 32, hidden 128,
  * num_hidden 2) and UpgradedMLP (NB c12:58-94: embed 128, hidden 256, num_hidden 3): cat[x, t_emb, b_emb] -> Linear/ReLU
  * stack -> logits[B,2].  Flat parameters in state_dict order: time_emb.weight, basis_emb.weight, then

@@ -525,3 +525,82 @@ def born_probabilities(psi_or_rho: np.ndarray, num_qubits: int, basis: str) -> n
         p = np.real(np.diag(U @ a @ U.conj().T))
     p = np.maximum(p, 0)
     return p / p.sum()
+
+
+# ============================================================================================ dataset unrolling
+# RQC/dataset.py:47-65 (SS/dataset.py:14-33): every measurement record's counts dict becomes `count` copies of
+# (bits[::-1], basis_idx); a DataLoader(shuffle=True) then draws batches (RQC/main.py:84-92).  The restatement keeps
+# the counts as a table and addresses shots by their position in the canonical unrolled order.
+def counts_rows_from_records(records: list, num_qubits: int):
+    """-> (hist int64[n_rows, 2^N], row_basis int64[n_rows], key_order list[list[int]]): one row per measurement
+    record in the reference's iteration order (circuit, then measurement); outcome index s = sum_q bit_q << q with
+    bits = reversed counts key (RQC/dataset.py:59); unknown bases are skipped (RQC/dataset.py:54);
+    key_order[row] = outcome indices in the counts dict's own order (the reference's within-row order)."""
+    names = basis_strings(num_qubits)
+    b2i = {b: i for i, b in enumerate(names)}
+    hist, row_basis, order = [], [], []
+    for circ in records:
+        for meas in circ.get("measurements", []):
+            if meas["basis"] not in b2i:
+                continue
+            row = np.zeros(1 << num_qubits, dtype=np.int64)
+            ko = []
+            for key, cnt in meas["counts"].items():
+                bits = [int(c) for c in key][::-1]
+                s = sum(v << i for i, v in enumerate(bits))
+                row[s] += int(cnt)
+                ko.append(s)
+            hist.append(row)
+            row_basis.append(b2i[meas["basis"]])
+            order.append(ko)
+    return np.array(hist, dtype=np.int64).reshape(-1, 1 << num_qubits), np.array(row_basis, dtype=np.int64), order
+
+
+def counts_unroll(hist: np.ndarray, row_basis: np.ndarray, num_qubits: int):
+    """Canonical unroll (row-major, outcomes ascending inside a row) -> (bits int64[total, N], basis int64[total])."""
+    flat = hist.reshape(-1)
+    idx = np.repeat(np.arange(flat.size), flat)
+    row, s = idx // hist.shape[1], idx % hist.shape[1]
+    bits = ((s[:, None] >> np.arange(num_qubits)) & 1).astype(np.int64)
+    return bits, np.asarray(row_basis)[row].astype(np.int64)
+
+
+def _fmix32(x):
+    x = np.asarray(x, dtype=np.uint64) & 0xFFFFFFFF
+    x ^= x >> np.uint64(16); x = (x * np.uint64(0x85EBCA6B)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(13); x = (x * np.uint64(0xC2B2AE35)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16)
+    return x
+
+
+def feistel_perm(i, total: int, seed: int, epoch: int) -> np.ndarray:
+    """Keyed bijection of [0, total): 4-round balanced Feistel network on 2h bits (4^h >= total) with cycle walking;
+    the stand-in for one epoch of DataLoader(shuffle=True) (include/ddqst.h, ddqst_counts_gather)."""
+    h = 1
+    while h < 31 and (1 << (2 * h)) < total:
+        h += 1
+    mask = np.uint64((1 << h) - 1)
+    base = (np.uint64(seed & 0xFFFFFFFF) ^ _fmix32(((seed >> 32) + 0x9E3779B9 * ((epoch + 1) & 0xFFFFFFFF)) & 0xFFFFFFFF))
+    keys = [_fmix32((int(base) + r * 0x85EBCA6B) & 0xFFFFFFFF) for r in range(4)]
+    x = np.asarray(i, dtype=np.uint64).copy().reshape(-1)
+    todo = np.ones(x.shape, dtype=bool)
+    while todo.any():
+        L, R = x[todo] >> np.uint64(h), x[todo] & mask
+        for r in range(4):
+            L, R = R, L ^ (_fmix32(R ^ keys[r]) & mask)
+        x[todo] = (L << np.uint64(h)) | R
+        todo = x >= np.uint64(total)
+    return x.astype(np.int64)
+
+
+def counts_batch(hist: np.ndarray, row_basis: np.ndarray, num_qubits: int, start: int, count: int, seed: int, epoch: int,
+                 permute: bool = True):
+    """Positions start..start+count-1 (mod total) of the (shuffled) unrolled dataset -> (packed int64[count], basis)."""
+    flat = hist.reshape(-1)
+    total = int(flat.sum())
+    p = (start + np.arange(count, dtype=np.int64)) % total
+    if permute:
+        p = feistel_perm(p, total, seed, epoch)
+    csum = np.cumsum(flat)
+    idx = np.searchsorted(csum, p, side="right")
+    return (idx % hist.shape[1]).astype(np.int64), np.asarray(row_basis)[idx // hist.shape[1]].astype(np.int64)
