@@ -129,8 +129,15 @@ def _prepare(synthetic_data, num_qubits: int):
         shots = torch.zeros(max(len(keys), 1), dtype=torch.int64, device=dev)
         for i, k in enumerate(keys):
             s = synthetic_data[k]
-            hist[i] = histogram_samples(s, N)
-            shots[i] = int(s.shape[0])
+            if getattr(s, "ndim", 2) == 1:                 # already a counts row uint32/int[2^N] (evaluate.format_raw_counts_for_inversion)
+                row = s if torch.is_tensor(s) else torch.from_numpy(np.ascontiguousarray(s))
+                row = row.to(dev)
+                row = row.view(torch.int32) if row.dtype == torch.uint32 else row.to(torch.int32)
+                hist[i] = row.view(torch.uint32)
+                shots[i] = int(row.to(torch.int64).sum().item())
+            else:
+                hist[i] = histogram_samples(s, N)
+                shots[i] = int(s.shape[0])
         canonical = keys == basis_strings(N)
         sel = None if canonical else torch.from_numpy(_compatible_slot_table(keys, N)).to(dev)
         return hist[:len(keys)].contiguous(), shots[:len(keys)].contiguous(), sel
