@@ -223,13 +223,10 @@ def run_native(args):
     # ---------------- recon + fidelity milliseconds (rank 0) ----------------
     recon = None
     if rank == 0:
-        from oracle import ddqst_oracle as orc
-        rng = np.random.default_rng(0)
-        psi = orc.haar_state(N, 0)
-        # synthetic random-circuit state measured in all 3^8 bases with 10^6 shots each
-        table = rng.multinomial(1_000_000, orc.born_probabilities_all(psi, N)).astype(np.int32)
-        h = torch.from_numpy(table).to(dev)
-        psi_d = torch.from_numpy(psi).to(dev)
+        # synthetic random-circuit state measured in all 3^8 bases with 10^6 shots each, generated on the
+        # device by the native generator (csrc/synth.cu): brick-wall random circuit, Born sampling from the Philox stream
+        psi_d = dq.synth_state(N, "rqc", depth=16, seed=args.seed, device=dev)
+        h = dq.born_histograms(psi_d, N, 1_000_000, seed=args.seed)
         for _ in range(2):
             rho = dq.linear_inversion(h, N)
             dq.state_fidelity(psi_d, rho)
@@ -240,7 +237,27 @@ def run_native(args):
         f = dq.state_fidelity(psi_d, rho)
         b.record()
         torch.cuda.synchronize()
-        recon = {"ms": a.elapsed_time(b), "what": "hist[6561,256] -> WHT -> rho[256,256] -> Jacobi PSD -> <psi|rho|psi>", "fidelity": f}
+        recon = {"ms": a.elapsed_time(b), "what": "hist[6561,256] -> WHT -> rho[256,256] -> Jacobi PSD -> <psi|rho|psi>", "fidelity": f,
+                 "input": "native generator: RQC depth 16, 6561 bases x 1e6 shots"}
+        # training step (T1) at the C4 architecture, per-GPU batch 1024, tensor-core path replayed from a CUDA graph
+        g = torch.Generator().manual_seed(1)
+        x0p = torch.randint(0, 1 << N, (1024,), generator=g).to(torch.uint16).to(dev)
+        b32 = torch.randint(0, NB, (1024,), generator=g).to(torch.int32).to(dev)
+        tmodel = reference_state_dict().to(dev)
+        tdiff = dq.DiscreteDiffusion(tmodel, T, dev, seed=args.seed, precision="bf16")
+        tg = tdiff.make_train_graph(x0p, b32, dq.NativeAdam(tmodel, lr=1e-3))
+        for _ in range(5):
+            tg.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            tg.replay()
+        b.record()
+        torch.cuda.synchronize()
+        recon["train_step_ms"] = a.elapsed_time(b) / 20
+        recon["train_step_what"] = "C4 model, batch 1024, tcgen05 bf16 fwd+bwd+Adam, CUDA-graph replay"
+        assert lib.ddqst_debug_tc_status() == 0, "tcgen05 pipeline timed out (train step)"
 
     # ---------------- roofline of the dominant kernel ----------------
     peaks, peak_src = measured_peaks()

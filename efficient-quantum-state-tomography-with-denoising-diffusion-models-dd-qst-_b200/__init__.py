@@ -11,6 +11,7 @@ from .dataset import QuantumStateDataset, load_circuit_records, state_vector_of
 from .diffusion import DiscreteDiffusion, NativeAdam, TrainGraph, cosine_schedule, linear_schedule
 from .distributed import all_reduce_histograms, sample_sharded, shard_range
 from .evaluate import calculate_z_bias, evaluate, evaluate_records, format_raw_counts_for_inversion, write_metrics_csv
+from .synthetic import born_histograms, counts_records, generate_synthetic_data, get_basis_combinations, synth_state
 from .model import ConditionalD3PM, pack_bits, unpack_bits
 from .notebook import BitstringDDM, SimpleMLP, UpgradedMLP
 from .reconstruct import (DensityMatrix, Statevector, basis_strings, get_coefficient, get_metrics, get_pauli_matrix,
@@ -21,5 +22,5 @@ __all__ = [
     "ConditionalD3PM", "DiscreteDiffusion", "NativeAdam", "TrainGraph", "cosine_schedule", "linear_schedule", "pack_bits", "unpack_bits",
     "DensityMatrix", "Statevector", "basis_strings", "get_coefficient", "get_metrics", "get_pauli_matrix",
     "histogram_samples", "linear_inversion", "linear_inversion_raw", "make_positive_semidefinite", "state_fidelity",
-    "calculate_z_bias", "evaluate", "evaluate_records", "format_raw_counts_for_inversion", "write_metrics_csv", "QuantumStateDataset", "load_circuit_records", "state_vector_of", "all_reduce_histograms", "sample_sharded", "shard_range", "build",
+    "calculate_z_bias", "evaluate", "evaluate_records", "format_raw_counts_for_inversion", "write_metrics_csv", "born_histograms", "counts_records", "generate_synthetic_data", "get_basis_combinations", "synth_state", "QuantumStateDataset", "load_circuit_records", "state_vector_of", "all_reduce_histograms", "sample_sharded", "shard_range", "build",
 ]

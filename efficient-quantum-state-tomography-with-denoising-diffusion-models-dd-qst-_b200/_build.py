@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libddqst.so")
-SOURCES = ["api.cu", "simt.cu", "recon.cu", "sampler_tc.cu", "train.cu", "train_tc.cu", "mlp.cu", "dataset.cu"]
+SOURCES = ["api.cu", "simt.cu", "recon.cu", "sampler_tc.cu", "train.cu", "train_tc.cu", "mlp.cu", "dataset.cu", "synth.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             sys.stderr.write(r.stderr)
 
-    with ThreadPoolExecutor(max_workers=7) as ex:
+    with ThreadPoolExecutor(max_workers=8) as ex:
         list(ex.map(compile_one, jobs))
     if force or jobs or _stale(LIB, objs):
         r = subprocess.run([_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",

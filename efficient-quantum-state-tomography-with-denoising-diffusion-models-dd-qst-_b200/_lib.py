@@ -61,6 +61,8 @@ SIGNATURES = {
     "ddqst_selftest_gemm_tc": (C.c_int, [_P, _P, C.c_int, C.c_int, _I32, _I32, _I32, _I32, _P, _P]),
     "ddqst_counts_scan": (C.c_int, [_P, _I64, _I32, _P, _P, _P]),
     "ddqst_counts_gather": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, C.c_int, _U64, _U64, _I64, _I64, _P, _P, _P, _P]),
+    "ddqst_synth_state": (C.c_int, [_I32, C.c_int, _I32, _U64, _P, _P]),
+    "ddqst_synth_born_histograms": (C.c_int, [_P, _I32, _P, _I32, _I64, _U64, C.c_double, C.c_double, _P, _P, _P]),
     "ddqst_workspace_bytes": (_I64, [C.c_int, _DP, _I64, C.c_int]),
     "ddqst_sample_host": (C.c_int, [_DP, _P, _P, C.c_int, C.c_int, _P, _I32, _I64, _I64, _U64, _P, _P, _P, _I64, _P]),
     "ddqst_mlp_param_count": (_I64, [_MP, _P]),

@@ -204,6 +204,19 @@ int ddqst_counts_gather(const uint32_t* cum, const int64_t* row_start, const int
                         int32_t num_qubits, int64_t total, int permute, uint64_t seed, uint64_t epoch, int64_t start,
                         int64_t count, uint16_t* out_x0_packed, int32_t* out_basis, int64_t* out_bits, void* stream);
 
+/* ---- synthetic measurement data (stand-in for the Qiskit-Aer generation of SS/data_gen.py:40-63,
+ * AS/data_gen.py:59-140, RQC/batch_build_dataset.py:53-144; qiskit is not a dependency of this library).
+ * synth_state: psi complex128[2^N] (bit i of the index = qubit i) <- kind 0 |0..0>, 1 |+..+>, 2 GHZ/Bell (SS/data_gen.py:22-26),
+ * 3 brick-wall random circuit of `depth` layers (random U3 per qubit, CZ on alternating neighbour pairs; gate angles from
+ * the Philox stream keyed by seed).  synth_born_histograms: for each listed basis (product-order index, NULL = 0..n-1)
+ * rotate into the basis (H for X, H.Sdg for Y), Born probabilities, noise (p_depolarizing: (1-p) P + p/2^N;
+ * p_readout: independent flip of every measured bit), then `shots` inverse-CDF draws -> hist[n_bases, 2^N] uint32
+ * ACCUMULATED (caller zeroes); probs_out (nullable) [n_bases, 2^N] float64 receives the sampled distributions. */
+int ddqst_synth_state(int32_t num_qubits, int kind, int32_t depth, uint64_t seed, double* psi, void* stream);
+int ddqst_synth_born_histograms(const double* psi, int32_t num_qubits, const int32_t* basis_ids, int32_t n_bases,
+                                int64_t shots, uint64_t seed, double p_depolarizing, double p_readout, uint32_t* hist,
+                                double* probs_out, void* stream);
+
 /* ---- M5 + the notebook DDM (single-qubit phase, config C1): SimpleMLP (NB c6:65-102: embed 32, hidden 128,
  * num_hidden 2) and UpgradedMLP (NB c12:58-94: embed 128, hidden 256, num_hidden 3): cat[x, t_emb, b_emb] -> Linear/ReLU
  * stack -> logits[B,2].  Flat parameters in state_dict order: time_emb.weight, basis_emb.weight, then

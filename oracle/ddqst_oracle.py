@@ -604,3 +604,93 @@ def counts_batch(hist: np.ndarray, row_basis: np.ndarray, num_qubits: int, start
     csum = np.cumsum(flat)
     idx = np.searchsorted(csum, p, side="right")
     return (idx % hist.shape[1]).astype(np.int64), np.asarray(row_basis)[idx // hist.shape[1]].astype(np.int64)
+
+
+# ============================================================================================ synthetic data (8f-4)
+# CPU restatement of csrc/synth.cu: special / random-circuit states and Born-rule sampling in Pauli bases.  The reference
+# generates this data with Qiskit Aer (SS/data_gen.py:13-63, AS/data_gen.py:59-140), which is not installable here; the
+# physics restated is its circuit: state preparation, then per qubit H (X) or Sdg.H (Y) before a Z measurement.
+SITE_SYNTH_DRAW, SITE_SYNTH_GATE = 16, 17
+
+
+def synth_state(num_qubits: int, kind: str, depth: int = 0, seed: int = 0) -> np.ndarray:
+    """'zero' | 'plus' | 'ghz' (= 'bell', SS/data_gen.py:22-26) | 'rqc' (brick-wall: random U3 per qubit, then CZ on
+    alternating neighbour pairs, per layer; angles from Philox counter (layer, qubit, SITE_SYNTH_GATE<<16, 0))."""
+    dim = 1 << num_qubits
+    psi = np.zeros(dim, dtype=complex)
+    psi[0] = 1.0
+    r = 0.70710678118654752440
+
+    def apply(psi, q, m):
+        v = psi.reshape(dim >> (q + 1), 2, 1 << q)
+        return np.einsum("ab,hbl->hal", m, v).reshape(dim)
+
+    if kind == "plus":
+        for q in range(num_qubits):
+            psi = apply(psi, q, np.array([[r, r], [r, -r]], dtype=complex))
+    elif kind in ("ghz", "bell"):
+        psi[:] = 0
+        psi[0] = psi[dim - 1] = r
+    elif kind == "rqc":
+        s = np.arange(dim)
+        for layer in range(depth):
+            for q in range(num_qubits):
+                w = philox4x32_10(np.array([[layer, q, SITE_SYNTH_GATE << 16, 0]], dtype=np.uint32),
+                                  np.array([[seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF]], dtype=np.uint32))[0]
+                theta = math.acos(1.0 - 2.0 * (float(w[0]) / 4294967296.0))
+                phi, lam = 2 * math.pi * (float(w[1]) / 4294967296.0), 2 * math.pi * (float(w[2]) / 4294967296.0)
+                c, sn = math.cos(0.5 * theta), math.sin(0.5 * theta)
+                U = np.array([[c, -complex(math.cos(lam), math.sin(lam)) * sn],
+                              [complex(math.cos(phi), math.sin(phi)) * sn, complex(math.cos(phi + lam), math.sin(phi + lam)) * c]])
+                psi = apply(psi, q, U)
+            sign = np.zeros(dim, dtype=np.int64)
+            for q in range(layer & 1, num_qubits - 1, 2):
+                sign ^= (s >> q) & (s >> (q + 1)) & 1
+            psi = np.where(sign == 1, -psi, psi)
+    elif kind != "zero":
+        raise ValueError(kind)
+    return psi
+
+
+def synth_probabilities(psi: np.ndarray, num_qubits: int, basis_ids, p_depol: float = 0.0, p_readout: float = 0.0) -> np.ndarray:
+    """Sampled distributions [len(basis_ids), 2^N] (unnormalised exactly as the kernel holds them)."""
+    names = basis_strings(num_qubits)
+    dim = 1 << num_qubits
+    r = 0.70710678118654752440
+    rot = {"X": np.array([[r, r], [r, -r]], dtype=complex), "Y": np.array([[r, -1j * r], [r, 1j * r]], dtype=complex)}
+    out = np.zeros((len(basis_ids), dim))
+    for k, b in enumerate(basis_ids):
+        amp = np.asarray(psi, dtype=complex).copy()
+        for q in range(num_qubits - 1, -1, -1):
+            letter = names[b][q]
+            if letter in rot:
+                amp = np.einsum("ab,hbl->hal", rot[letter], amp.reshape(dim >> (q + 1), 2, 1 << q)).reshape(dim)
+        p = (1.0 - p_depol) * (amp.real ** 2 + amp.imag ** 2) + p_depol / dim
+        if p_readout > 0:
+            for q in range(num_qubits):
+                v = p.reshape(dim >> (q + 1), 2, 1 << q)
+                p = np.stack([(1 - p_readout) * v[:, 0] + p_readout * v[:, 1], p_readout * v[:, 0] + (1 - p_readout) * v[:, 1]],
+                             axis=1).reshape(dim)
+        out[k] = p
+    return out
+
+
+def synth_histograms(probs: np.ndarray, basis_ids, shots: int, seed: int) -> np.ndarray:
+    """Inverse-CDF draws from the Philox stream: draw j of a basis uses pair k = j // 2, counter (k_lo, basis,
+    SITE_SYNTH_DRAW<<16, k_hi); u = 53 bits of (x,y) for even j, (z,w) for odd j; outcome = first s with cdf[s] > u*cdf[-1]."""
+    n_b, dim = probs.shape
+    hist = np.zeros((n_b, dim), dtype=np.int64)
+    npairs = (shots + 1) // 2
+    k = np.arange(npairs, dtype=np.uint64)
+    for i, b in enumerate(basis_ids):
+        cdf = np.cumsum(probs[i])
+        ctr = np.stack([(k & np.uint64(0xFFFFFFFF)).astype(np.uint32), np.full(npairs, b, dtype=np.uint32),
+                        np.full(npairs, SITE_SYNTH_DRAW << 16, dtype=np.uint32), (k >> np.uint64(32)).astype(np.uint32)], axis=1)
+        key = np.tile(np.array([[seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF]], dtype=np.uint32), (npairs, 1))
+        w = philox4x32_10(ctr, key).astype(np.uint64)
+        u0 = (((w[:, 0] << np.uint64(32)) | w[:, 1]) >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+        u1 = (((w[:, 2] << np.uint64(32)) | w[:, 3]) >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+        u = np.stack([u0, u1], axis=1).reshape(-1)[:shots] * cdf[-1]
+        idx = np.minimum(np.searchsorted(cdf, u, side="right"), dim - 1)
+        hist[i] = np.bincount(idx, minlength=dim)
+    return hist
