@@ -239,7 +239,9 @@ def run_native(args):
         torch.cuda.synchronize()
         recon = {"ms": a.elapsed_time(b), "what": "hist[6561,256] -> WHT -> rho[256,256] -> Jacobi PSD -> <psi|rho|psi>", "fidelity": f,
                  "input": "native generator: RQC depth 16, 6561 bases x 1e6 shots"}
-        # training step (T1) at the C4 architecture, per-GPU batch 1024, tensor-core path replayed from a CUDA graph
+    if rank == 0 and world == 1:
+        # training step (T1) at the C4 architecture, batch 1024, tensor-core path replayed from a CUDA graph (single-GPU
+        # runs only: inside a multi-rank job the step would all-reduce its gradients and wait for the other ranks)
         g = torch.Generator().manual_seed(1)
         x0p = torch.randint(0, 1 << N, (1024,), generator=g).to(torch.uint16).to(dev)
         b32 = torch.randint(0, NB, (1024,), generator=g).to(torch.int32).to(dev)
