@@ -2,8 +2,11 @@
 // PSD projection by a parallel one-sided Jacobi eigensolver (R4), fidelity (F1) and get_metrics.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "sampler_tc.cuh"
+#include "tc_ptx.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -629,6 +632,226 @@ __global__ void partial_trace_kernel(const double2* __restrict__ rho, int dim, i
 
 // Hermitian eigendecomposition of A[n,n] (n a power of two >= 2): evals[n], VT (rows = eigenvectors).
 // ws: GT[n*n] double2, then JacobiCtl.
+// ---- systolic form (Brent-Luk ring) for n <= 256: warp k of the cluster owns two columns IN REGISTERS (top_k, bot_k).
+// After each rotation the columns move one place along a ring (top_0 fixed; top row shifts right, bottom row left), so
+// over n-1 steps every pair meets exactly once and everything is back home.  Columns travel as st.async stores into the
+// neighbour warp's shared-memory inbox (distributed shared memory when the neighbour sits in another CTA), completing a
+// transaction count on the neighbour's mbarrier: no global memory, no fence and no cluster-wide barrier inside a sweep --
+// a warp only ever waits for its two neighbours.  Two inboxes per warp (step parity): a neighbour can run at most one
+// step ahead because it needs this warp's previous output, so an inbox is always drained before it is refilled.
+// fp64 reciprocal square root / reciprocal from the fp32 special-function unit + Newton steps (argument within fp32
+// range): the rotation angle needs only a few of these instead of full IEEE divisions and square roots, whose
+// dependent instruction chains dominated the step time
+__device__ __forceinline__ double jr_rsqrt(double x) {
+  double y = (double)__frsqrt_rn((float)x);
+  const double hx = 0.5 * x;
+#pragma unroll
+  for (int it = 0; it < 3; ++it) y = y * fma(-hx, y * y, 1.5);
+  return y;
+}
+__device__ __forceinline__ double jr_rcp(double x) {
+  double y = (double)__frcp_rn((float)x);
+#pragma unroll
+  for (int it = 0; it < 3; ++it) y = y * fma(-x, y, 2.0);
+  return y;
+}
+__device__ __forceinline__ uint32_t jr_mapa(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void jr_send(uint32_t raddr, double2 v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
+               ::"r"(raddr), "d"(v.x), "d"(v.y), "r"(rbar) : "memory");
+}
+#ifdef DDQST_JR_PROFILE
+__device__ long long g_jr_prof[8];
+#define JR_STAMP(i) do { if (k == 1 && lane == 0) { long long _t = clock64(); g_jr_prof[i] += _t - _t0; _t0 = _t; } } while (0)
+#else
+#define JR_STAMP(i) do { } while (0)
+#endif
+template <int EPL>
+__global__ void __launch_bounds__(kJcThreads) jacobi_ring_kernel(double2* __restrict__ GT, int n, int max_sweeps, double tol,
+                                                                JacobiCtl* ctl) {
+  extern __shared__ __align__(16) uint8_t jr_smem[];
+  constexpr int COLB = EPL * 32 * 16;                 // one column slot
+  constexpr int WPC = kJcThreads / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int h = n / 2, k = (int)crank * WPC + warp;
+  const bool active = k < h;
+  const uint32_t smem0 = smem_u32(jr_smem);
+  const uint32_t bars0 = smem0 + WPC * 4 * COLB;
+  auto inbox = [&](int w, int par, int slot) { return smem0 + (uint32_t)(((w * 2 + par) * 2 + slot) * COLB); };   // slot 0 = top, 1 = bot
+  auto bar = [&](int w, int par) { return bars0 + (uint32_t)((w * 2 + par) * 8); };
+  const uint32_t colbytes = (uint32_t)n * 16u;
+  const uint32_t expect = (active && h >= 2) ? ((k == 0 || k == h - 1) ? colbytes : 2u * colbytes) : 0u;
+  if (lane == 0) {
+    mbar_init(bar(warp, 0), 1); mbar_init(bar(warp, 1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (expect) { mbar_expect_tx(bar(warp, 0), expect); mbar_expect_tx(bar(warp, 1), expect); }
+  }
+  double2 x[EPL], y[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int i = lane + 32 * e;
+    const bool ok = active && i < n;
+    x[e] = ok ? GT[(int64_t)k * n + i] : make_double2(0.0, 0.0);
+    y[e] = ok ? GT[(int64_t)(k + h) * n + i] : make_double2(0.0, 0.0);
+  }
+  // where this warp's columns go after a step
+  const int top_to = (k >= 1 && k <= h - 2) ? k + 1 : -1;            // into that warp's top inbox
+  const int bot_to = k >= 1 ? k - 1 : (h >= 2 ? 1 : -1);             // bot inbox of k-1; warp 0's bottom becomes top of warp 1
+  const int bot_slot = k >= 1 ? 1 : 0;
+  uint32_t top_addr[2] = {0, 0}, top_bar[2] = {0, 0}, bot_addr[2] = {0, 0}, bot_bar[2] = {0, 0};
+  if (active) {
+#pragma unroll
+    for (int par = 0; par < 2; ++par) {
+      if (top_to >= 0) {
+        top_addr[par] = jr_mapa(inbox(top_to % WPC, par, 0), (uint32_t)(top_to / WPC));
+        top_bar[par] = jr_mapa(bar(top_to % WPC, par), (uint32_t)(top_to / WPC));
+      }
+      if (bot_to >= 0) {
+        bot_addr[par] = jr_mapa(inbox(bot_to % WPC, par, bot_slot), (uint32_t)(bot_to / WPC));
+        bot_bar[par] = jr_mapa(bar(bot_to % WPC, par), (uint32_t)(bot_to / WPC));
+      }
+    }
+  }
+  __syncwarp();
+  jc_cluster_barrier();                               // every inbox barrier is initialised and armed before the first send
+  const int m = n - 1;
+  int sweep = 0;
+  uint32_t g = 0;                                     // global step counter (inbox parity, barrier phase)
+  for (; sweep < max_sweeps; ++sweep) {
+    int rot = 0;
+    if (active) {
+      for (int step = 0; step < m; ++step, ++g) {
+#ifdef DDQST_JR_PROFILE
+        long long _t0 = clock64();
+#endif
+        double a = 0.0, b = 0.0, gr = 0.0, gi = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          a += x[e].x * x[e].x + x[e].y * x[e].y;
+          b += y[e].x * y[e].x + y[e].y * y[e].y;
+          gr += x[e].x * y[e].x + x[e].y * y[e].y;     // conj(x)*y
+          gi += x[e].x * y[e].y - x[e].y * y[e].x;
+        }
+        a = warp_sum(a); b = warp_sum(b); gr = warp_sum(gr); gi = warp_sum(gi);
+        a = __shfl_sync(0xFFFFFFFFu, a, 0); b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        gr = __shfl_sync(0xFFFFFFFFu, gr, 0); gi = __shfl_sync(0xFFFFFFFFu, gi, 0);
+        JR_STAMP(0);
+        const double g2 = gr * gr + gi * gi;
+        if (g2 > tol * tol * a * b && g2 > 1e-60) {        // |gamma| > tol sqrt(a b)
+          double c, s, pr, pi;
+          if (g2 > 1e-30 && g2 < 1e30) {
+            const double inv_g = jr_rsqrt(g2);              // 1 / |gamma|
+            const double zeta = 0.5 * (b - a) * inv_g, az = fabs(zeta);
+            // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)); beyond |zeta| = 1e7 that is 1/(2 zeta) to 1e-14
+            const double az2 = fma(az, az, 1.0);
+            const double at = az < 1e7 ? jr_rcp(az + az2 * jr_rsqrt(az2)) : 0.5 * jr_rcp(az);
+            const double t = zeta >= 0.0 ? at : -at;
+            c = jr_rsqrt(fma(t, t, 1.0)); s = c * t;
+            pr = gr * inv_g; pi = -gi * inv_g;              // e^{-i phi} = conj(gamma)/|gamma|
+          } else {                                          // outside the fp32 seed range: IEEE path
+            const double gabs = sqrt(g2);
+            const double zeta = (b - a) / (2.0 * gabs);
+            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            c = 1.0 / sqrt(1.0 + t * t); s = c * t;
+            pr = gr / gabs; pi = -gi / gabs;
+          }
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) {
+            const double2 yr = make_double2(y[e].x * pr - y[e].y * pi, y[e].x * pi + y[e].y * pr);
+            const double2 xn = make_double2(c * x[e].x - s * yr.x, c * x[e].y - s * yr.y);
+            y[e] = make_double2(s * x[e].x + c * yr.x, s * x[e].y + c * yr.y);
+            x[e] = xn;
+          }
+          ++rot;
+        }
+        JR_STAMP(1);
+        if (h >= 2) {
+          const uint32_t par = (g + 1u) & 1u;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) {
+            const int i = lane + 32 * e;
+            if (i < n) {
+              if (top_to >= 0) jr_send(top_addr[par] + (uint32_t)i * 16u, x[e], top_bar[par]);
+              jr_send(bot_addr[par] + (uint32_t)i * 16u, y[e], bot_bar[par]);
+            }
+          }
+          if (k == h - 1) {                           // the last warp's top turns the corner into its own bottom slot
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) y[e] = x[e];
+          }
+          JR_STAMP(2);
+          mbar_wait(bar(warp, (int)par), (g >> 1) & 1u, 60);
+          JR_STAMP(3);
+          const uint8_t* in_top = jr_smem + ((warp * 2 + par) * 2 + 0) * COLB;
+          const uint8_t* in_bot = jr_smem + ((warp * 2 + par) * 2 + 1) * COLB;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) {
+            const int i = lane + 32 * e;
+            if (i < n) {
+              if (k >= 1) x[e] = *reinterpret_cast<const double2*>(in_top + i * 16);
+              if (k <= h - 2) y[e] = *reinterpret_cast<const double2*>(in_bot + i * 16);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_expect_tx(bar(warp, (int)par), expect);     // re-arm for the step after next
+          JR_STAMP(4);
+        }
+      }
+      if (lane == 0 && rot > 0) atomicAdd(&ctl->rotations[sweep], rot);
+    }
+    jc_cluster_barrier();
+    const int total = __ldcg(&ctl->rotations[sweep]);
+    if (total == 0) { ++sweep; break; }
+  }
+  if (active) {                                       // after whole sweeps every column is back in its home slot
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int i = lane + 32 * e;
+      if (i < n) { GT[(int64_t)k * n + i] = x[e]; GT[(int64_t)(k + h) * n + i] = y[e]; }
+    }
+  }
+  if (k == 0 && lane == 0) ctl->sweeps_done = sweep;
+  jc_cluster_barrier();                               // nobody exits while a peer could still write into its inbox
+}
+
+template <int EPL>
+static int launch_jacobi_ring(double2* GT, int n, int max_sweeps, double tol, JacobiCtl* ctl, cudaStream_t s, bool* launched) {
+  constexpr int smem = (kJcThreads / 32) * 4 * EPL * 32 * 16 + 256;
+  *launched = false;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DDQST_CUDA_OK(cudaFuncSetAttribute(jacobi_ring_kernel<EPL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    DDQST_CUDA_OK(cudaFuncSetAttribute(jacobi_ring_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  int csize = (n / 2 + kJcThreads / 32 - 1) / (kJcThreads / 32);
+  if (csize < 1) csize = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)csize);
+  cfg.blockDim = dim3(kJcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int fits = 0;
+  if (cudaOccupancyMaxActiveClusters(&fits, jacobi_ring_kernel<EPL>, &cfg) != cudaSuccess || fits < 1) {
+    (void)cudaGetLastError();
+    return DDQST_OK;                                  // the caller falls back to the L2-resident cluster kernel
+  }
+  DDQST_CUDA_OK(cudaLaunchKernelEx(&cfg, jacobi_ring_kernel<EPL>, GT, n, max_sweeps, tol, ctl));
+  *launched = true;
+  return DDQST_OK;
+}
+
 template <int EPL>
 static int launch_jacobi_cluster(double2* GT, int n, int max_sweeps, double tol, JacobiCtl* ctl, int csize, cudaStream_t s) {
   static bool attr_set = false;
@@ -670,7 +893,22 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
   DDQST_LAUNCH_OK();
   int max_sweeps = 60;
   double tol = 1e-15;
-  if (n <= 256) {
+  bool ring_done = false;
+  const char* ring_env = getenv("DDQST_JACOBI_RING");          // DDQST_JACOBI_RING=0 keeps the L2-resident kernel (debugging aid)
+  if (ring_env == nullptr || ring_env[0] != '0') {
+    if (n <= 256) {
+      const int epl = n <= 32 ? 1 : n / 32;
+      switch (epl) {
+        case 1: DDQST_TRY(launch_jacobi_ring<1>(GT, n, max_sweeps, tol, ctl, s, &ring_done)); break;
+        case 2: DDQST_TRY(launch_jacobi_ring<2>(GT, n, max_sweeps, tol, ctl, s, &ring_done)); break;
+        case 4: DDQST_TRY(launch_jacobi_ring<4>(GT, n, max_sweeps, tol, ctl, s, &ring_done)); break;
+        default: DDQST_TRY(launch_jacobi_ring<8>(GT, n, max_sweeps, tol, ctl, s, &ring_done)); break;
+      }
+    }
+  }
+  if (ring_done) {
+    // eigenpairs are read off G below
+  } else if (n <= 256) {
     // one warp per column pair, 8 warps per CTA, up to 16 CTAs in the cluster
     int csize = (n / 2 + kJcThreads / 32 - 1) / (kJcThreads / 32);
     if (csize < 1) csize = 1;
@@ -696,6 +934,17 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
   DDQST_LAUNCH_OK();
   return DDQST_OK;
 }
+
+int recon_tc_abort_fetch() { return tc_abort_fetch(); }
+#ifdef DDQST_JR_PROFILE
+extern "C" int ddqst_debug_jr_profile(long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_jr_prof, sizeof(long long) * 8);
+  long long z[8] = {0};
+  cudaMemcpyToSymbol(g_jr_prof, z, sizeof(z));
+  return 0;
+}
+#endif
 
 }  // namespace ddqst
 

@@ -781,7 +781,8 @@ int ddqst_selftest_umma(const float* a, const uint16_t* w_bf16, int32_t m_tiles,
 int ddqst_debug_tc_status(void) {
   int a = tc_abort_fetch();          // this TU's kernels (samplers, UMMA self tests)
   int b = train_tc_abort_fetch();    // train_tc.cu's GEMM kernels
-  return a != 0 ? a : b;
+  int c = recon_tc_abort_fetch();    // recon.cu's ring Jacobi
+  return a != 0 ? a : (b != 0 ? b : c);
 }
 
 }  // extern "C"

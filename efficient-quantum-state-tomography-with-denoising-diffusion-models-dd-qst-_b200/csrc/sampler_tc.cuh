@@ -24,6 +24,7 @@ int sampler_tc_forward(const ddqst_dims* d, const char* pack, const PackLayout& 
 int64_t train_workspace_bytes(const ddqst_dims* d, int64_t batch);
 int64_t train_tc_workspace_bytes(const ddqst_dims* d, int64_t batch);
 int train_tc_abort_fetch();
+int recon_tc_abort_fetch();   // recon.cu (ring Jacobi inbox barriers)
 
 // shared by the fp32 reverse-step kernel and the tcgen05 epilogue so both draw identically
 // logit(q, c) supplies logits[q][c]; returns the packed x_{t-1}
