@@ -131,6 +131,20 @@ class QuantumStateDataset:
         if self.device.type == "cuda":
             self._upload()
 
+    @classmethod
+    def from_counts_table(cls, hist: torch.Tensor, num_qubits: int, row_basis=None, device="cuda", seed: int = 1234):
+        """Dataset over an existing counts table ``uint32/int[n_rows, 2^N]`` (e.g. ``generate_synthetic_data``'s device
+        output or a sampler histogram) without going through Python dicts; ``row_basis`` defaults to the row index."""
+        self = cls([], num_qubits, device="cpu", seed=seed)
+        h = hist.detach()
+        h = h if h.dtype == torch.uint32 else h.to(torch.int32).view(torch.uint32)
+        self.hist = h.clone()
+        self.n_rows = int(h.shape[0])
+        rb = torch.arange(self.n_rows, dtype=torch.int32) if row_basis is None else torch.as_tensor(row_basis, dtype=torch.int32)
+        self.row_basis = rb.clone()
+        self._total = int(h.view(torch.int32).to(torch.int64).sum().item())
+        return self.to(device)
+
     # ------------------------------------------------------------------ device tables
     def _upload(self):
         lib = _lib.load()

@@ -139,3 +139,9 @@ def test_device_dataset_edge_cases(dq):
     assert x0.tolist() == [2, 2, 2, 2] and kb.tolist() == [8, 8, 8, 8]
     with pytest.raises(FileNotFoundError):
         dq.QuantumStateDataset("/nonexistent/path.pt", 2)
+    # straight from a device counts table (no dict round trip)
+    tab = torch.from_numpy(hist.astype(np.int32)).cuda()
+    ds2 = dq.QuantumStateDataset.from_counts_table(tab, n, row_basis=row_basis, seed=1)
+    assert len(ds2) == len(ds)
+    x2, k2 = ds2.batch(3, 777)
+    assert torch.equal(x2, x0) and torch.equal(k2, kb)
