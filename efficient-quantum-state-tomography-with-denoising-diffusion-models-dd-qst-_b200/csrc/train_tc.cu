@@ -359,7 +359,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------ small CUDA-core kernels
-// xin = token embeddings (variant B), cond = [time_emb[t] | basis_emb[basis]], ind[b, v*N+q] = (bit_q == v); all bf16
+// xin = token embeddings (variant B only; x_emb == nullptr for variant A), cond = [time_emb[t] | basis_emb[basis]], ind[b, v*N+q] = (bit_q == v); all bf16
 __global__ void gather_tc_kernel(int N, int E, const float* __restrict__ x_emb, const float* __restrict__ time_emb,
                                  const float* __restrict__ basis_emb, const uint16_t* __restrict__ xt,
                                  const int32_t* __restrict__ t, const int32_t* __restrict__ basis,
@@ -372,15 +372,41 @@ __global__ void gather_tc_kernel(int N, int E, const float* __restrict__ x_emb, 
     cond[i * 2 * E + e] = __float2bfloat16(te[e]);
     cond[i * 2 * E + E + e] = __float2bfloat16(be[e]);
   }
-  for (int j = threadIdx.x; j < N * E; j += blockDim.x) {
-    int q = j / E, e = j - q * E;
-    xin[i * N * E + j] = __float2bfloat16(x_emb[((bits >> q) & 1u) * E + e]);
+  if (x_emb) {
+    for (int j = threadIdx.x; j < N * E; j += blockDim.x) {
+      int q = j / E, e = j - q * E;
+      xin[i * N * E + j] = __float2bfloat16(x_emb[((bits >> q) & 1u) * E + e]);
+    }
   }
   if (threadIdx.x < 32) {
     int j = threadIdx.x, v = j / N, q = j - v * N;
     float f = (j < 2 * N && ((bits >> q) & 1u) == (uint32_t)v) ? 1.f : 0.f;
     ind[i * 32 + j] = __float2bfloat16(f);
   }
+}
+
+// Variant A front end (SS/model.py:56,70: input_proj = Linear(N, H) on x.float()): K = N is far too small for a tensor-core
+// tile, so the layer is a CUDA-core elementwise pass with the same fused FiLM epilogue as TE_IN:
+//   h0[b,c] = in_b[c] + sum_q bit_q(b) Win[c,q] ;  a0 = h0 (1 + gamma_0) + beta_0
+__global__ void in_a_forward_kernel(int64_t B, int N, int H, const float* __restrict__ in_w, const float* __restrict__ in_b,
+                                    const uint16_t* __restrict__ xt, const float* __restrict__ gb0, float* __restrict__ h0,
+                                    __nv_bfloat16* __restrict__ a0) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * H) return;
+  const int64_t b = e / H;
+  const int c = (int)(e - b * H);
+  const uint32_t bits = xt[b];
+  float v = in_b[c];
+  for (int q = 0; q < N; ++q) v += ((bits >> q) & 1u) ? in_w[c * N + q] : 0.f;
+  h0[e] = v;
+  a0[e] = __float2bfloat16(fmaf(v, 1.0f + gb0[b * 2 * H + c], gb0[b * 2 * H + H + c]));
+}
+// dWin[c,q] = sum_b dh0[b,c] bit_q(b) = S[N + q, c]  (S = ind^T . dh0, rows N.. = the "bit == 1" indicators)
+__global__ void in_a_wgrad_kernel(int N, int H, const float* __restrict__ S, float* __restrict__ g_in_w) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= H * N) return;
+  const int c = e / N, q = e - c * N;
+  g_in_w[e] = S[(int64_t)(N + q) * H + c];
 }
 
 __global__ void loss_finish_tc_kernel(const float* __restrict__ part, int n, float inv_total, float* __restrict__ out) {
@@ -590,11 +616,9 @@ int64_t train_tc_workspace_bytes(const ddqst_dims* d, int64_t batch) {
 int train_tc_abort_fetch() { return tc_abort_fetch(); }
 
 static int train_tc_supported(const ddqst_dims* d, const ParamLayout& pr) {
-  DDQST_REQUIRE(d->variant == DDQST_VARIANT_B, DDQST_EUNSUPPORTED,
-                "tensor-core training is built for the RQC model variant (x_emb front end); use precision fp32 for variant A");
   DDQST_REQUIRE(d->hidden_dim % 64 == 0 && d->embed_dim % 16 == 0 && d->num_qubits <= 15 && 2 * d->num_blocks <= kGtMaxZ,
                 DDQST_EUNSUPPORTED, "tensor-core training needs hidden_dim %% 64 == 0, embed_dim %% 16 == 0, num_qubits <= 15, num_blocks <= 16");
-  bool ok = pr.in_w % 8 == 0 && pr.head_w % 8 == 0;
+  bool ok = (d->variant == DDQST_VARIANT_A || pr.in_w % 8 == 0) && pr.head_w % 8 == 0;
   for (int l = 0; l < d->num_blocks; ++l) ok = ok && pr.film_w[l] % 8 == 0 && pr.w1[l] % 8 == 0 && pr.w2[l] % 8 == 0;
   DDQST_REQUIRE(ok, DDQST_EUNSUPPORTED, "parameter offsets are not 16-byte aligned in the bf16 shadow");
   return DDQST_OK;
@@ -611,6 +635,7 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
   DDQST_REQUIRE(workspace && ws_bytes >= w.bf_total * 2 + w.f_total * 4 + 1024, DDQST_EWORKSPACE,
                 "tensor-core train step needs %lld workspace bytes, got %lld", (long long)(w.bf_total * 2 + w.f_total * 4 + 1024), (long long)ws_bytes);
   const int N = d->num_qubits, E = d->embed_dim, H = d->hidden_dim, L = d->num_blocks, XIN = N * E;
+  const bool var_b = d->variant == DDQST_VARIANT_B;
   char* base = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
   __nv_bfloat16* bf = (__nv_bfloat16*)base;
   float* fp = (float*)(base + align_up(w.bf_total * 2, 1024));
@@ -627,8 +652,8 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
     return g;
   };
 
-  gather_tc_kernel<<<(unsigned)B, 128, 0, s>>>(N, E, params + pr.x_emb, params + pr.time_emb, params + pr.basis_emb, xt, t, basis,
-                                               xin, cond, ind);
+  gather_tc_kernel<<<(unsigned)B, 128, 0, s>>>(N, E, var_b ? params + pr.x_emb : nullptr, params + pr.time_emb, params + pr.basis_emb,
+                                               xt, t, basis, xin, cond, ind);
   DDQST_LAUNCH_OK();
 
   // ------------------------------------------------------------------ forward
@@ -640,10 +665,13 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
     HostOperand Bo{shadow + pr.film_w[0], 0, 2 * H, 2 * E, L, 2 * E, blk_stride > 0 ? blk_stride : (int64_t)2 * H * 2 * E, 0, 1};
     DDQST_TRY(launch_gemm<TE_STORE>(A, Bo, g, L, s));
   }
-  {  // h0, a0
+  if (var_b) {  // h0, a0
     TcGemm g = base_gemm((int)B, H, XIN);
     g.bias = params + pr.in_b; g.o0 = h; g.f1 = gb; g.b0 = act;
     DDQST_TRY(launch_gemm<TE_IN>(op_k(xin, B, XIN, XIN), op_k(shadow + pr.in_w, H, XIN, XIN), g, 1, s));
+  } else {
+    in_a_forward_kernel<<<(unsigned)((B * H + 255) / 256), 256, 0, s>>>(B, N, H, params + pr.in_w, params + pr.in_b, xt, gb, h, act);
+    DDQST_LAUNCH_OK();
   }
   for (int l = 0; l < L; ++l) {
     {
@@ -716,7 +744,7 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
     HostOperand Bo{cond, 1, 2 * E, B, 1, 2 * E, B * 2 * E, 0, 0};
     DDQST_TRY(launch_gemm<TE_STORE>(A, Bo, g, L, s));
   }
-  {  // Win
+  if (var_b) {  // Win
     TcGemm g = base_gemm(H, XIN, (int)B);
     g.o0 = grads + pr.in_w; g.ld = XIN;
     DDQST_TRY(launch_gemm<TE_STORE>(op_mn(dh0, H, B, H), op_mn(xin, XIN, B, XIN), g, 1, s));
@@ -746,7 +774,8 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
     colsum_bf16_kernel<<<dim3((unsigned)((maxc + 63) / 64), (unsigned)n), 256, 0, s>>>(T, B);
     DDQST_LAUNCH_OK();
   }
-  xemb_grad_kernel<<<dim3((unsigned)N, (unsigned)(H / 64)), 128, 0, s>>>(N, E, H, S, params + pr.in_w, grads + pr.x_emb);
+  if (var_b) xemb_grad_kernel<<<dim3((unsigned)N, (unsigned)(H / 64)), 128, 0, s>>>(N, E, H, S, params + pr.in_w, grads + pr.x_emb);
+  else in_a_wgrad_kernel<<<(unsigned)((H * N + 127) / 128), 128, 0, s>>>(N, H, S, grads + pr.in_w);
   DDQST_LAUNCH_OK();
   return DDQST_OK;
 }

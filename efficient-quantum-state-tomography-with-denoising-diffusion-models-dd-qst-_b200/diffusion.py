@@ -235,10 +235,10 @@ class DiscreteDiffusion:
 
     # ------------------------------------------------------------------ training step (T1)
     def train_precision(self) -> str:
-        """'bf16' (tcgen05 GEMMs, ddqst_train_forward_backward_tc) when this object samples in bf16 and the model is the
-        RQC variant with tensor-core-friendly dims, else 'fp32' (CUDA-core exact path)."""
+        """'bf16' (tcgen05 GEMMs, ddqst_train_forward_backward_tc) when this object samples in bf16 and the model has
+        tensor-core-friendly dims, else 'fp32' (CUDA-core exact path)."""
         m = self.model
-        ok = (self.precision == "bf16" and m.variant == "B" and m.hidden_dim % 64 == 0 and m.embed_dim % 16 == 0
+        ok = (self.precision == "bf16" and m.hidden_dim % 64 == 0 and m.embed_dim % 16 == 0
               and m.num_qubits <= 15 and m.num_blocks <= 16)
         return "bf16" if ok else "fp32"
 

@@ -87,11 +87,13 @@ def _compare(dq, m, B, T, tol_loss, tol_grad, seed=0):
     return worst
 
 
-def test_train_tc_matches_fp32_small(dq):
-    """The reference-fixture model (N=3, E=16, H=64, L=2): ragged batch, tiny K/N dims -> every TMA tail path."""
-    z = load_golden("model_B_small.npz")
+@pytest.mark.parametrize("tag", ["B", "A"])
+def test_train_tc_matches_fp32_small(dq, tag):
+    """The reference-fixture models (N=3, E=16, H=64, L=2; B = RQC x_emb front end, A = SS Linear(N,H) front end):
+    ragged batch, tiny K/N dims -> every TMA tail path."""
+    z = load_golden(f"model_{tag}_small.npz")
     N, NB, T, E, H, L = (int(v) for v in z["dims"])
-    m = dq.ConditionalD3PM(N, NB, T, E, H, L, variant="B")
+    m = dq.ConditionalD3PM(N, NB, T, E, H, L, variant=tag)
     m.load_state_dict(golden_state_dict(z, "sd."))
     m = m.cuda()
     _compare(dq, m, 300, T, tol_loss=5e-3, tol_grad=3e-2)
@@ -128,6 +130,25 @@ def test_train_tc_steps_track_fp32(dq):
     assert rel < 2e-2, rel
     # the bf16 shadow the Adam kernel maintains equals a fresh cast of the parameters
     assert torch.equal(mtc.bf16_shadow(), mtc.flat_params.to(torch.bfloat16))
+
+
+def test_train_tc_variant_a_adamw_tracks_reference(dq):
+    """SS phase: variant A model, linear schedule, AdamW(lr 1e-4, wd 0.01) (SS/main.py:77) on the reference fixture."""
+    z = load_golden("model_A_small.npz")
+    N, NB, T, E, H, L = (int(v) for v in z["dims"])
+    m = dq.ConditionalD3PM(N, NB, T, E, H, L, variant="A")
+    m.load_state_dict(golden_state_dict(z, "sd."))
+    m = m.cuda()
+    diff = dq.DiscreteDiffusion(m, T, "cuda", schedule="linear", seed=int(z["train_seed"][0]))
+    assert diff.train_precision() == "bf16"
+    opt = dq.NativeAdam(m, lr=1e-4, weight_decay=0.01, decoupled=True)
+    x0, b0 = torch.from_numpy(z["train_x0"]).cuda(), torch.from_numpy(z["train_basis"]).cuda()
+    losses = [diff.train_step(x0, b0, opt).item() for _ in range(3)]
+    assert dq._lib.load().ddqst_debug_tc_status() == 0
+    assert np.allclose(losses, z["train_losses"], rtol=1e-2), (losses, z["train_losses"])
+    want = golden_state_dict(z, "trained.")
+    for k, v in want.items():
+        assert (m.state_dict()[k].cpu() - v).abs().max().item() < 2.5e-4, k      # AdamW moves each weight by <= lr per step
 
 
 def test_train_graph_replay_matches_eager(dq):
