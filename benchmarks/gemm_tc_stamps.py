@@ -1,5 +1,15 @@
+#!/usr/bin/env python
+"""Where a training-GEMM CTA spends its cycles: clock64 stamps of CTA (0,0,0) of gemm_tc_kernel (train_tc.cu) taken at
+kernel start, after the prologue (barrier init + TMEM alloc), after griddepcontrol.wait, at the first / last K-block the MMA
+warp sees, when the epilogue gets the accumulator, after the epilogue and after TMEM dealloc -- printed relative to the
+first stamp.  (K-block period = (stamp[4] - stamp[3]) / (K/64 - 1); round 1: 480 cycles at a 128x64 tile against a
+128-cycle MMA floor: per-SM operand ingest ~60 B/clk and the dependent tcgen05.mma chain ~120 cycles each.)
+
+    python benchmarks/gemm_tc_stamps.py
+"""
 import ctypes as C, torch, sys
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ddqst_b200 as dq
 lib = dq._lib.load()
 f = lib.ddqst_selftest_gemm_tc_dbg
