@@ -79,6 +79,7 @@ struct TcGemm {
   int nq, E, flag;     // qubits (TE_HEAD), embed dim (TE_DCOND), variant flag (TE_W2: 1 = FiLM next, TE_BW1: 1 = l > 0)
   float scale;         // TE_HEAD: loss_scale / (B*N)
   long long* dbg;      // optional [8] clock64 stamps of CTA (0,0,0) (self test only)
+  long long* trace;    // optional [4] %globaltimer ns of CTA (0,0,0): entry, after griddepcontrol.wait, epilogue done, EPI (benchmarks/train_trace.py)
 };
 
 template <int BN>
@@ -126,7 +127,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   // only touched after griddepcontrol.wait below (= the previous kernel has completed and flushed)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const bool dbg = G.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const bool trace = G.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
   if (dbg && tid == 0) G.dbg[0] = clock64();
+  if (trace) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); G.trace[0] = t; }
   if (tid == 0) {
     for (int i = 0; i < kGtStages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     mbar_init(bar_acc, 1);
@@ -144,6 +147,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (dbg && tid == 0) G.dbg[1] = clock64();
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (dbg && tid == 0) G.dbg[2] = clock64();
+  if (trace) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); G.trace[1] = t; }
 
   if (warp == 4) {
     // =============================== TMA producer ===============================
@@ -207,6 +211,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // =============================== epilogue: thread = output row ===============================
     const int r = m0 + warp * 32 + lane;
     const bool rv = r < G.M;
+    // Epilogue operands (residual stream, FiLM vectors, saved pre-activations) do not depend on the accumulator: the
+    // loads of a 32-column chunk are all issued together -- for the first chunk before the accumulator wait, so they
+    // fly under the main loop -- instead of in dependent load -> use -> store -> load rounds (each round is a full
+    // L2 latency with only 128 loading threads per CTA).
+    float q0[32], q1[32], q2[32], q3[32];
+    auto issue_loads = [&](int c0) {
+      if (!rv) return;
+      const int c = n0 + c0;
+      const int64_t e = (int64_t)r * G.ld + c, ge = (int64_t)r * G.ldg + c;
+      if (EPI == TE_IN) { ld32(G.f1 + ge, q0); ld32(G.f1 + ge + G.ld, q1); }
+      if (EPI == TE_W2) { ld32(G.f0 + e, q0); if (G.flag) { ld32(G.f1 + ge, q1); ld32(G.f1 + ge + G.ld, q2); } }
+      if (EPI == TE_BHEAD || EPI == TE_BW2) ld32(G.f0 + e, q0);
+      if (EPI == TE_BW1) { ld32(G.f1 + e, q0); ld32(G.f0 + ge, q1); ld32(G.f3 + e, q2); if (G.flag) ld32(G.f2 + e, q3); }
+    };
+    issue_loads(0);
     mbar_wait(bar_acc, 0, 42);
     tc_fence_after();
     if (dbg && tid == 0) G.dbg[5] = clock64();
@@ -273,14 +292,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       } else if (rv) {
         const int64_t e = (int64_t)r * G.ld + c;          // element offset in [rows, H] arrays
         if (EPI == TE_IN) {
-          float g[32], be[32];
-          ld32(G.f1 + (int64_t)r * G.ldg + c, g);
-          ld32(G.f1 + (int64_t)r * G.ldg + G.ld + c, be);
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += __ldg(G.bias + c + i);
           st32(G.o0 + e, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], 1.0f + g[i], be[i]);
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], 1.0f + q0[i], q1[i]);
           st32_bf16(G.b0 + e, v);
         } else if (EPI == TE_W1) {
 #pragma unroll
@@ -290,56 +306,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int i = 0; i < 32; ++i) v[i] *= sigmoid_fast(v[i]);
           st32_bf16(G.b0 + e, v);
         } else if (EPI == TE_W2) {
-          float hin[32];
-          ld32(G.f0 + e, hin);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += hin[i] + __ldg(G.bias + c + i);
+          for (int i = 0; i < 32; ++i) v[i] += q0[i] + __ldg(G.bias + c + i);
           st32(G.o0 + e, v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= sigmoid_fast(v[i]);
           st32(G.o1 + e, v);
           if (G.flag) {
-            float g[32], be[32];
-            ld32(G.f1 + (int64_t)r * G.ldg + c, g);
-            ld32(G.f1 + (int64_t)r * G.ldg + G.ld + c, be);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], 1.0f + g[i], be[i]);
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], 1.0f + q1[i], q2[i]);
           }
           st32_bf16(G.b0 + e, v);
         } else if (EPI == TE_BHEAD) {
-          float zz[32];
-          ld32(G.f0 + e, zz);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= dsilu_fast(zz[i]);
+          for (int i = 0; i < 32; ++i) v[i] *= dsilu_fast(q0[i]);
           st32(G.o0 + e, v);
           st32_bf16(G.b0 + e, v);
         } else if (EPI == TE_BW2) {
-          float zz[32];
-          ld32(G.f0 + e, zz);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= dsilu_fast(zz[i]);
+          for (int i = 0; i < 32; ++i) v[i] *= dsilu_fast(q0[i]);
           st32_bf16(G.b0 + e, v);
         } else if (EPI == TE_BW1) {
-          // v = da.  f0 = gb_l (gamma | beta), f1 = h_l, f2 = z2_{l-1}, f3 = residual gradient (dz2_l)
-          float t[32], w[32];
-          ld32(G.f1 + e, t);                                   // h_in
+          // v = da.  q0 = h_l, q1 = gamma_l, q2 = residual gradient (dz2_l), q3 = z2_{l-1}
 #pragma unroll
-          for (int i = 0; i < 32; ++i) w[i] = v[i] * t[i];      // dgamma = da * h_in
-          st32_bf16(G.b1 + (int64_t)r * G.ldg + c, w);
+          for (int i = 0; i < 32; ++i) q0[i] *= v[i];           // dgamma = da * h_in
+          st32_bf16(G.b1 + (int64_t)r * G.ldg + c, q0);
           st32_bf16(G.b1 + (int64_t)r * G.ldg + G.ld + c, v);   // dbeta = da
-          ld32(G.f0 + (int64_t)r * G.ldg + c, t);               // gamma
-          ld32(G.f3 + e, w);                                    // residual gradient
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], 1.0f + t[i], w[i]);
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], 1.0f + q1[i], q2[i]);
           if (G.flag) {
-            ld32(G.f2 + e, t);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= dsilu_fast(t[i]);
+            for (int i = 0; i < 32; ++i) v[i] *= dsilu_fast(q3[i]);
             st32(G.o0 + e, v);
           }
           st32_bf16(G.b0 + e, v);
         }
       }
+      if (c0 + 32 < BN) issue_loads(c0 + 32);        // the q arrays are dead here; these loads fly under the next tcgen05.ld
     }
     if (EPI == TE_HEAD) {
 #pragma unroll
@@ -350,6 +353,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   }
   if (dbg && tid == 0) G.dbg[6] = clock64();
+  if (trace) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); G.trace[2] = t; G.trace[3] = EPI; }
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
@@ -542,6 +546,10 @@ struct HostOperand {
 static HostOperand op_k(const void* base, int64_t mn, int64_t k, int64_t ld) { return HostOperand{base, 0, mn, k, 1, ld, mn * ld, 0, 0}; }
 static HostOperand op_mn(const void* base, int64_t mn, int64_t k, int64_t ld) { return HostOperand{base, 1, mn, k, 1, ld, k * ld, 0, 0}; }
 
+// debugging aid: when a trace buffer is registered, GEMM launch i of a step writes its timestamps to buf[4*i .. 4*i+3]
+static long long* g_trace_buf = nullptr;
+static int g_trace_idx = 0, g_trace_cap = 0;
+
 // DDQST_TC_PDL=0 launches the GEMMs fully serialised (debugging aid)
 static bool tc_pdl_enabled() {
   static int v = -1;
@@ -558,6 +566,7 @@ static int launch_gemm_bn(const HostOperand& A, const HostOperand& B, TcGemm g, 
   else DDQST_TRY(make_map3(&mb, B.base, B.k, B.mn, B.batch, B.ld, B.batch_stride, BN));
   g.a = TcOperand{A.mn_major, A.kmod, A.zmul};
   g.b = TcOperand{B.mn_major, B.kmod, B.zmul};
+  if (g_trace_buf && g_trace_idx < g_trace_cap) g.trace = g_trace_buf + 4 * (g_trace_idx++);
   static bool attr_set = false;
   if (!attr_set) {
     DDQST_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes<BN>()));
@@ -785,6 +794,12 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
 using namespace ddqst;
 
 extern "C" {
+
+// register (or clear, with NULL) a device buffer of 4*cap int64 for per-GEMM %globaltimer stamps; resets the launch index
+int ddqst_debug_tc_trace(long long* buf, int32_t cap) {
+  g_trace_buf = buf; g_trace_cap = cap; g_trace_idx = 0;
+  return DDQST_OK;
+}
 
 int ddqst_cast_bf16(const float* src, uint16_t* dst, int64_t n, void* stream) {
   DDQST_TRY(check_arch());
