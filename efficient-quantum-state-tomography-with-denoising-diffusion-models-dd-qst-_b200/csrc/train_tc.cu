@@ -108,9 +108,11 @@ __device__ __forceinline__ void st32_bf16(__nv_bfloat16* p, const float (&v)[32]
                                                 pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
 }
 
+// one 128 x BN output tile (bx, by) of batch entry bz; the whole CTA calls it
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kGtThreads)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcGemm G) {
+__device__ __forceinline__ void gemm_tile(const CUtensorMap* mapA_p, const CUtensorMap* mapB_p, const TcGemm& G, int bx, int by, int bz) {
+  const CUtensorMap& mapA = *mapA_p;
+  const CUtensorMap& mapB = *mapB_p;
   constexpr int STAGE = gt_stage_bytes<BN>();
   constexpr int kGtStages = gt_stages<BN>();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -120,14 +122,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   float* s_red = (float*)(tmem_slot + 4);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kGtStages), bar_acc = smem_u32(bars + 2 * kGtStages);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN, z = blockIdx.z;
+  const int m0 = bx * 128, n0 = by * BN, z = bz;
   const int KB = (G.K + 63) >> 6;
 
   // programmatic dependent launch: let the next kernel of the stream start its prologue now; our own inputs are
   // only touched after griddepcontrol.wait below (= the previous kernel has completed and flushed)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const bool dbg = G.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-  const bool trace = G.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+  const bool dbg = G.dbg != nullptr && bx == 0 && by == 0 && bz == 0;
+  const bool trace = G.trace != nullptr && bx == 0 && by == 0 && bz == 0 && tid == 0;
   if (dbg && tid == 0) G.dbg[0] = clock64();
   if (trace) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); G.trace[0] = t; }
   if (tid == 0) {
@@ -349,7 +351,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xFFFFFFFFu, loss_acc, o);
       if (lane == 0) s_red[warp] = loss_acc;
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (tid == 0) G.o1[blockIdx.x] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+      if (tid == 0) G.o1[bx] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
     }
   }
   if (dbg && tid == 0) G.dbg[6] = clock64();
@@ -360,6 +362,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
   }
   if (dbg && tid == 160) G.dbg[7] = clock64();
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGtThreads)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcGemm G) {
+  gemm_tile<BN, EPI>(&mapA, &mapB, G, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
+}
+
+// Several independent TE_STORE problems (the weight-gradient GEMMs of one step) in ONE launch: CTA i belongs to the group
+// whose [start, start + tiles) range contains i.  Saves the launch + drain of four small kernels per step.
+constexpr int kGtMaxGroup = 5;
+struct TcGroup {
+  CUtensorMap mapA[kGtMaxGroup], mapB[kGtMaxGroup];
+  TcGemm g[kGtMaxGroup];
+  int start[kGtMaxGroup + 1];
+  int tiles_m[kGtMaxGroup], tiles_n[kGtMaxGroup];
+  int n;
+};
+template <int BN>
+__global__ void __launch_bounds__(kGtThreads) gemm_tc_group_kernel(const __grid_constant__ TcGroup P) {
+  int i = 0;
+  const int lin = (int)blockIdx.x;
+#pragma unroll
+  for (int k = 1; k < kGtMaxGroup; ++k)
+    if (k < P.n && lin >= P.start[k]) i = k;
+  const int local = lin - P.start[i];
+  const int tm = P.tiles_m[i], tn = P.tiles_n[i];
+  gemm_tile<BN, TE_STORE>(&P.mapA[i], &P.mapB[i], P.g[i], local % tm, (local / tm) % tn, local / (tm * tn));
 }
 
 // ------------------------------------------------------------------------------------ small CUDA-core kernels
@@ -586,6 +616,50 @@ static int launch_gemm_bn(const HostOperand& A, const HostOperand& B, TcGemm g, 
   return DDQST_OK;
 }
 
+// ---- grouped TE_STORE launch (BN = 64)
+struct GroupBuilder {
+  TcGroup grp{};
+  int total = 0;
+  int add(const HostOperand& A, const HostOperand& B, TcGemm g, int zcount) {
+    const int i = grp.n;
+    if (i >= kGtMaxGroup) { set_error("too many problems in one grouped GEMM launch"); return DDQST_EINVAL_SHAPE; }
+    if (A.mn_major) DDQST_TRY(make_map3(&grp.mapA[i], A.base, A.mn, A.k, A.batch, A.ld, A.batch_stride, 64));
+    else DDQST_TRY(make_map3(&grp.mapA[i], A.base, A.k, A.mn, A.batch, A.ld, A.batch_stride, 128));
+    if (B.mn_major) DDQST_TRY(make_map3(&grp.mapB[i], B.base, B.mn, B.k, B.batch, B.ld, B.batch_stride, 64));
+    else DDQST_TRY(make_map3(&grp.mapB[i], B.base, B.k, B.mn, B.batch, B.ld, B.batch_stride, 64));
+    g.a = TcOperand{A.mn_major, A.kmod, A.zmul};
+    g.b = TcOperand{B.mn_major, B.kmod, B.zmul};
+    if (g_trace_buf && g_trace_idx < g_trace_cap) g.trace = g_trace_buf + 4 * (g_trace_idx++);
+    grp.g[i] = g;
+    grp.tiles_m[i] = (g.M + 127) / 128;
+    grp.tiles_n[i] = (g.N + 63) / 64;
+    grp.start[i] = total;
+    total += grp.tiles_m[i] * grp.tiles_n[i] * zcount;
+    grp.start[i + 1] = total;
+    grp.n = i + 1;
+    return DDQST_OK;
+  }
+  int launch(cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      DDQST_CUDA_OK(cudaFuncSetAttribute(gemm_tc_group_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes<64>()));
+      attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)total);
+    cfg.blockDim = dim3(kGtThreads);
+    cfg.dynamicSmemBytes = gt_smem_bytes<64>();
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = tc_pdl_enabled() ? 1 : 0;
+    DDQST_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_group_kernel<64>, grp));
+    return DDQST_OK;
+  }
+};
+
 // BN = 128 when the grid still covers the machine (or N is not a multiple of 64-wide tiles anyway), else 64
 template <int EPI>
 static int launch_gemm(const HostOperand& A, const HostOperand& B, const TcGemm& g, int zcount, cudaStream_t s) {
@@ -737,36 +811,41 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
     DDQST_TRY(launch_gemm<TE_DCOND>(A, Bo, g, L, s));
   }
   // ------------------------------------------------------------------ backward: weight gradients (dY^T . X over the batch)
-  {  // W1_l, W2_l for every block: z = 2l (dz1_l, a_l), 2l+1 (dz2_l, u_l)
-    TcGemm g = base_gemm(H, H, (int)B);
-    g.o0 = grads;
-    for (int l = 0; l < L; ++l) { g.out_zoff[2 * l] = pr.w1[l]; g.out_zoff[2 * l + 1] = pr.w2[l]; }
-    HostOperand A{dz, 1, H, B, 2 * L, H, BH, 0, 1};
-    HostOperand Bo{act, 1, H, B, 2 * L, H, BH, 0, 1};
-    DDQST_TRY(launch_gemm<TE_STORE>(A, Bo, g, 2 * L, s));
-  }
-  {  // Wfilm_l
-    TcGemm g = base_gemm(2 * H, 2 * E, (int)B);
-    g.o0 = grads; g.ld = 2 * E;
-    for (int l = 0; l < L; ++l) g.out_zoff[l] = pr.film_w[l];
-    HostOperand A{dgb, 1, 2 * H, B, L, 2 * H, BG, 0, 1};
-    HostOperand Bo{cond, 1, 2 * E, B, 1, 2 * E, B * 2 * E, 0, 0};
-    DDQST_TRY(launch_gemm<TE_STORE>(A, Bo, g, L, s));
-  }
-  if (var_b) {  // Win
-    TcGemm g = base_gemm(H, XIN, (int)B);
-    g.o0 = grads + pr.in_w; g.ld = XIN;
-    DDQST_TRY(launch_gemm<TE_STORE>(op_mn(dh0, H, B, H), op_mn(xin, XIN, B, XIN), g, 1, s));
-  }
-  {  // Whead
-    TcGemm g = base_gemm(2 * N, H, (int)B);
-    g.o0 = grads + pr.head_w; g.ld = H;
-    DDQST_TRY(launch_gemm<TE_STORE>(op_mn(dlog, 2 * N, B, 32), op_mn(hL, H, B, H), g, 1, s));
-  }
-  {  // S = ind^T . dh0  (for the x_emb gradient)
-    TcGemm g = base_gemm(2 * N, H, (int)B);
-    g.o0 = S; g.ld = H;
-    DDQST_TRY(launch_gemm<TE_STORE>(op_mn(ind, 2 * N, B, 32), op_mn(dh0, H, B, H), g, 1, s));
+  // five independent problems, one grouped launch
+  {
+    GroupBuilder grp;
+    {  // W1_l, W2_l for every block: z = 2l (dz1_l, a_l), 2l+1 (dz2_l, u_l)
+      TcGemm g = base_gemm(H, H, (int)B);
+      g.o0 = grads;
+      for (int l = 0; l < L; ++l) { g.out_zoff[2 * l] = pr.w1[l]; g.out_zoff[2 * l + 1] = pr.w2[l]; }
+      HostOperand A{dz, 1, H, B, 2 * L, H, BH, 0, 1};
+      HostOperand Bo{act, 1, H, B, 2 * L, H, BH, 0, 1};
+      DDQST_TRY(grp.add(A, Bo, g, 2 * L));
+    }
+    {  // Wfilm_l
+      TcGemm g = base_gemm(2 * H, 2 * E, (int)B);
+      g.o0 = grads; g.ld = 2 * E;
+      for (int l = 0; l < L; ++l) g.out_zoff[l] = pr.film_w[l];
+      HostOperand A{dgb, 1, 2 * H, B, L, 2 * H, BG, 0, 1};
+      HostOperand Bo{cond, 1, 2 * E, B, 1, 2 * E, B * 2 * E, 0, 0};
+      DDQST_TRY(grp.add(A, Bo, g, L));
+    }
+    if (var_b) {  // Win
+      TcGemm g = base_gemm(H, XIN, (int)B);
+      g.o0 = grads + pr.in_w; g.ld = XIN;
+      DDQST_TRY(grp.add(op_mn(dh0, H, B, H), op_mn(xin, XIN, B, XIN), g, 1));
+    }
+    {  // Whead
+      TcGemm g = base_gemm(2 * N, H, (int)B);
+      g.o0 = grads + pr.head_w; g.ld = H;
+      DDQST_TRY(grp.add(op_mn(dlog, 2 * N, B, 32), op_mn(hL, H, B, H), g, 1));
+    }
+    {  // S = ind^T . dh0  (for the x_emb gradient / the variant-A input weights)
+      TcGemm g = base_gemm(2 * N, H, (int)B);
+      g.o0 = S; g.ld = H;
+      DDQST_TRY(grp.add(op_mn(ind, 2 * N, B, 32), op_mn(dh0, H, B, H), g, 1));
+    }
+    DDQST_TRY(grp.launch(s));
   }
   // ------------------------------------------------------------------ bias gradients, x_emb gradient
   {
