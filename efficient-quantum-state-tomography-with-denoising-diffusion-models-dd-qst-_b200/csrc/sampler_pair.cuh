@@ -291,18 +291,24 @@ sampler_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
 #pragma unroll
       for (int c = 0; c < NCH; ++c) signal_ready(c);
 
-      for (int t = P.t_start; t >= P.t_end; --t) {
-        {
-          const float* tt = P.Tt + (int64_t)t * L * 2 * H;
-          const float* tb = P.Tb + (int64_t)basis * L * 2 * H;
-          for (int i = tid; i < L * 2 * H; i += kEpiThreads) {
-            int l = i / (2 * H), j = i - l * 2 * H;
-            float v = __ldg(tt + i) + __ldg(tb + i);
-            if (j < H) sG1[l * H + j] = 1.0f + v;
-            else sBeta[l * H + j - H] = v;
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      // FiLM vectors of a step: 1 + gamma and beta for every block, = Tt[t] + Tb[basis].  Step t_start's are loaded here by
+      // everyone; the following steps' are loaded by the twelve non-worker warps while the four worker warps run the head
+      // epilogue of the step before (every FiLM row is dead once the last block's E2 is done), so the L2 latency of the
+      // table rows no longer sits between two steps.
+      auto load_film = [&](int t, int first, int stride) {
+        const float* tt = P.Tt + (int64_t)t * L * 2 * H;
+        const float* tb = P.Tb + (int64_t)basis * L * 2 * H;
+        for (int i = first; i < L * 2 * H; i += stride) {
+          int l = i / (2 * H), j = i - l * 2 * H;
+          float v = __ldg(tt + i) + __ldg(tb + i);
+          if (j < H) sG1[l * H + j] = 1.0f + v;
+          else sBeta[l * H + j - H] = v;
         }
+      };
+      load_film(P.t_start, tid, kEpiThreads);
+
+      for (int t = P.t_start; t >= P.t_end; --t) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");     // this step's FiLM rows are in shared memory
         // ---- input epilogue: h0 -> residual registers, a = film_0(h0)
 #pragma unroll
         for (int n = 0; n < NCH; ++n) {
@@ -384,7 +390,8 @@ sampler_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           ++slot;
         }
 
-        // ---- head epilogue
+        // ---- head epilogue (worker warps); everyone else fetches the next step's FiLM rows meanwhile
+        if (!worker && t > P.t_end) load_film(t - 1, tid - 128, kEpiThreads - 128);
         wait_acc(0, 11);
         if (worker) {
           uint32_t r[16], r2[16];
