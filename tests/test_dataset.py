@@ -144,4 +144,5 @@ def test_device_dataset_edge_cases(dq):
     ds2 = dq.QuantumStateDataset.from_counts_table(tab, n, row_basis=row_basis, seed=1)
     assert len(ds2) == len(ds)
     x2, k2 = ds2.batch(3, 777)
-    assert torch.equal(x2, x0) and torch.equal(k2, kb)
+    x1, k1 = ds.batch(3, 777)
+    assert torch.equal(x2, x1) and torch.equal(k2, k1)
