@@ -106,6 +106,14 @@ def test_train_tc_matches_fp32_c4(dq):
     _compare(dq, m, 1024, 100, tol_loss=5e-3, tol_grad=3e-2)
 
 
+def test_train_tc_matches_fp32_wide_tiles(dq):
+    """Batch large enough that the fused-epilogue GEMMs take the 128x128 tile path (4 accumulator chunks per row, 6-stage
+    ring) and the grouped weight-gradient launch spans several waves; ragged last row tile (6200 = 48*128 + 56)."""
+    torch.manual_seed(5)
+    m = dq.ConditionalD3PM(4, 81, 50, 32, 256, 2).cuda()
+    _compare(dq, m, 6200, 50, tol_loss=5e-3, tol_grad=3e-2, seed=2)
+
+
 def test_train_tc_steps_track_fp32(dq):
     """30 optimiser steps on the same data and noise stream: the tensor-core run's loss curve follows the fp32 run's."""
     torch.manual_seed(1)
