@@ -351,11 +351,13 @@ __global__ void __launch_bounds__(256) fidelity_pure_kernel(const double2* __res
 // ------------------------------------------------------------------------------------ Jacobi eigensolver
 // One-sided (Hestenes) Jacobi on A' = A + sigma*I (positive definite by construction, so singular values
 // are eigenvalues and no sign ambiguity arises).  GT holds the columns of G = A'V as contiguous rows.
-struct JacobiCtl {
+struct JacobiCtl {            // lives in the 512 bytes between G and the eigenvalue array: keep it below that
   double sigma;
   int rotations[64];
   int sweeps_done;
+  unsigned int max_ratio2[48];     // ring kernel: per sweep, float bits of max |gamma|^2 / (a b) seen BEFORE rotating
 };
+static_assert(sizeof(JacobiCtl) <= 512, "JacobiCtl must fit the gap in the eigensolver workspace");
 
 __global__ void jacobi_init_kernel(const double2* __restrict__ A, int n, double2* __restrict__ GT, JacobiCtl* ctl) {
   // single block: Frobenius norm -> sigma, then GT = columns of A + sigma I.  The eigenvector matrix is never
@@ -371,6 +373,7 @@ __global__ void jacobi_init_kernel(const double2* __restrict__ A, int n, double2
     ctl->sigma = sigma;
     ctl->sweeps_done = 0;
     for (int i = 0; i < 64; ++i) ctl->rotations[i] = 0;
+    for (int i = 0; i < 48; ++i) ctl->max_ratio2[i] = 0u;
   }
   for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
     int j = (int)(e / n), i = (int)(e % n);
@@ -725,6 +728,7 @@ __global__ void __launch_bounds__(kJcThreads) jacobi_ring_kernel(double2* __rest
   uint32_t g = 0;                                     // global step counter (inbox parity, barrier phase)
   for (; sweep < max_sweeps; ++sweep) {
     int rot = 0;
+    float worst = 0.f;              // max |gamma|^2 / (a b) this warp met in the sweep
     if (active) {
       for (int step = 0; step < m; ++step, ++g) {
 #ifdef DDQST_JR_PROFILE
@@ -743,6 +747,7 @@ __global__ void __launch_bounds__(kJcThreads) jacobi_ring_kernel(double2* __rest
         gr = __shfl_sync(0xFFFFFFFFu, gr, 0); gi = __shfl_sync(0xFFFFFFFFu, gi, 0);
         JR_STAMP(0);
         const double g2 = gr * gr + gi * gi;
+        worst = fmaxf(worst, (float)(g2 / (a * b)));
         if (g2 > tol * tol * a * b && g2 > 1e-60) {        // |gamma| > tol sqrt(a b)
           double c, s, pr, pi;
           if (g2 > 1e-30 && g2 < 1e30) {
@@ -804,10 +809,14 @@ __global__ void __launch_bounds__(kJcThreads) jacobi_ring_kernel(double2* __rest
         }
       }
       if (lane == 0 && rot > 0) atomicAdd(&ctl->rotations[sweep], rot);
+      if (lane == 0 && sweep < 48) atomicMax(&ctl->max_ratio2[sweep], __float_as_uint(worst));
     }
     jc_cluster_barrier();
     const int total = __ldcg(&ctl->rotations[sweep]);
     if (total == 0) { ++sweep; break; }
+    // Quadratic convergence: a sweep that started with every |gamma| / sqrt(a b) below 1e-7 leaves them at ~1e-14 --
+    // already at the rounding level of the columns -- so the all-quiet verification sweep that would follow is skipped.
+    if (sweep < 48 && __uint_as_float(__ldcg(&ctl->max_ratio2[sweep])) < 1e-14f) { ++sweep; break; }
   }
   if (active) {                                       // after whole sweeps every column is back in its home slot
 #pragma unroll
