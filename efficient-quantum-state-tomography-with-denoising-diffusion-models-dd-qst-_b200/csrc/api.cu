@@ -432,13 +432,19 @@ __global__ void pack_bits_kernel(const int64_t* __restrict__ bits, int64_t batch
 
 __global__ void unpack_bits_kernel(const void* __restrict__ packed, int elem_bytes, int64_t total, int N,
                                    int64_t* __restrict__ bits) {
-  // one thread per output element: coalesced 8-byte stores
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // one thread per PAIR of output elements: coalesced 16-byte stores (the int64[B,N] output is 64x the input bytes, so
+  // the store width is what matters); an odd total leaves one element for the last thread
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e = 2 * p;
   if (e >= total) return;
-  int64_t i = e / N;
-  int q = (int)(e - i * N);
-  uint32_t v = elem_bytes == 1 ? ((const uint8_t*)packed)[i] : ((const uint16_t*)packed)[i];
-  bits[e] = (v >> q) & 1u;
+  auto bit_of = [&](int64_t el) -> long long {
+    const int64_t i = el / N;
+    const int q = (int)(el - i * N);
+    const uint32_t v = elem_bytes == 1 ? ((const uint8_t*)packed)[i] : ((const uint16_t*)packed)[i];
+    return (long long)((v >> q) & 1u);
+  };
+  if (e + 1 < total) *reinterpret_cast<longlong2*>(bits + e) = make_longlong2(bit_of(e), bit_of(e + 1));
+  else bits[e] = bit_of(e);
 }
 }  // namespace ddqst
 
@@ -482,7 +488,8 @@ int ddqst_unpack_bits(const void* packed, int elem_bytes, int64_t batch, int32_t
   DDQST_REQUIRE(num_qubits >= 1 && num_qubits <= 16 && batch >= 0 && (elem_bytes == 1 || elem_bytes == 2), DDQST_EINVAL_SHAPE, "bad shape");
   if (batch == 0) return DDQST_OK;
   int64_t total = batch * num_qubits;
-  unpack_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(packed, elem_bytes, total, num_qubits, bits);
+  DDQST_REQUIRE(((uintptr_t)bits & 15) == 0, DDQST_EINVAL_SHAPE, "bits must be 16-byte aligned");
+  unpack_bits_kernel<<<(unsigned)(((total + 1) / 2 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(packed, elem_bytes, total, num_qubits, bits);
   DDQST_LAUNCH_OK();
   return DDQST_OK;
 }
