@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--embed", type=int, default=64)
     ap.add_argument("--hidden", type=int, default=256)
     ap.add_argument("--blocks", type=int, default=3)
+    ap.add_argument("--state", default="rqc", help="rqc | ghz | bell | plus (SS/data_gen.py state types)")
+    ap.add_argument("--variant", default="B", help="B = RQC model (x_emb front end, cosine schedule, posterior sampler); "
+                                                   "A = SS model (Linear(N,H) front end, linear schedule, re-noise sampler, AdamW)")
     ap.add_argument("--noise", default="readout")
     ap.add_argument("--error-rate", type=float, default=0.02)
     ap.add_argument("--seed", type=int, default=7)
@@ -51,7 +54,7 @@ def main():
         return out
 
     # 1. data: clean state + noisy measurement counts in every basis (stands in for the Aer generation)
-    psi = dq.synth_state(N, "rqc", args.depth, args.seed, dev)
+    psi = dq.synth_state(N, args.state, args.depth, args.seed, dev)
     hist = timed("generate_counts", lambda: dq.born_histograms(psi, N, args.shots_train, args.seed, None, args.noise, args.error_rate))
     clean = dq.born_histograms(psi, N, args.shots_train, args.seed + 1)
     # 2. dataset (the reference's record format, then the device-side table)
@@ -61,9 +64,10 @@ def main():
     res["train_shots"] = len(ds)
     # 3. training
     torch.manual_seed(args.seed)
-    model = dq.ConditionalD3PM(N, NB, args.T, args.embed, args.hidden, args.blocks).to(dev)
-    diff = dq.DiscreteDiffusion(model, args.T, dev, seed=args.seed, precision="bf16")
-    opt = dq.NativeAdam(model, lr=1e-3)
+    model = dq.ConditionalD3PM(N, NB, args.T, args.embed, args.hidden, args.blocks, variant=args.variant).to(dev)
+    diff = dq.DiscreteDiffusion(model, args.T, dev, schedule="cosine" if args.variant == "B" else "linear", seed=args.seed,
+                                precision="bf16")
+    opt = dq.NativeAdam(model, lr=1e-3) if args.variant == "B" else dq.NativeAdam(model, lr=1e-4, weight_decay=0.01, decoupled=True)
     x0_s, b_s = ds.batch(0, args.batch)
     prec = args.train_precision or diff.train_precision()
     graph = diff.make_train_graph(x0_s, b_s, opt) if prec == "bf16" else None

@@ -70,3 +70,25 @@ def test_reconstruction_identical(phases):
     shuffled = dict(reversed(list(data.items())))
     ref = phases["RQC"]["reconstruct"].linear_inversion(shuffled, N).data
     assert np.abs(ref - orc.linear_inversion_literal(shuffled, N, True)).max() < 1e-13
+
+
+def test_shipped_datapoints_directory_loads_through_the_dataset_surface():
+    """Config C3's data: the whole Datapoints/rqc_N3_data directory (21 .pt shards that reference qiskit classes) through
+    QuantumStateDataset's own loader (no GPU needed for the counts table): 363 circuits x 27 bases x 1024 shots."""
+    import os
+    import numpy as np
+    import ddqst_b200 as dq
+    from oracle import ref_harness as rh
+    path = os.path.join(rh.REF_ROOT, "Datapoints", "rqc_N3_data")
+    if not os.path.isdir(path):
+        pytest.skip("reference Datapoints not mounted")
+    ds = dq.QuantumStateDataset(path, 3, device="cpu")
+    assert len(ds) == 363 * 27 * 1024 == 10_036_224
+    assert ds.n_rows == 363 * 27
+    h = ds.hist.view(torch.int32).numpy()
+    assert (h.sum(axis=1) == 1024).all()
+    assert np.array_equal(ds.row_basis.numpy().reshape(363, 27), np.tile(np.arange(27), (363, 1)))
+    # the same records through the oracle's restatement of RQC/dataset.py
+    recs = rh.load_datapoints(os.path.join(path, "part_0.pt"))
+    want, rb, _ = orc.counts_rows_from_records(recs, 3)
+    assert np.array_equal(h[: want.shape[0]], want)
