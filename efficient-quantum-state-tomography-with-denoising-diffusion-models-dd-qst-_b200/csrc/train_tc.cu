@@ -447,18 +447,21 @@ __global__ void loss_finish_tc_kernel(const float* __restrict__ part, int n, flo
   if (threadIdx.x == 0 && blockIdx.x == 0) { double s = 0.0; for (int i = 0; i < n; ++i) s += part[i]; out[0] = (float)(s * inv_total); }
 }
 
-// bias gradients: deterministic column sums of the bf16 dY arrays
+// bias gradients: column sums of the bf16 dY arrays.  blockIdx.z splits the rows into chunks whose partial sums are added
+// atomically into the (pre-zeroed) gradient -- the reduction over 1024+ rows is latency-bound, so it wants many blocks
 struct ColsumTask { const __nv_bfloat16* p; int64_t ld; int cols; float* out; };
 struct ColsumTasks { ColsumTask t[56]; };
-__global__ void colsum_bf16_kernel(const __grid_constant__ ColsumTasks T, int64_t rows) {
+__global__ void colsum_bf16_kernel(const __grid_constant__ ColsumTasks T, int64_t rows, int64_t rows_per_chunk) {
   const ColsumTask k = T.t[blockIdx.y];
   const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
   if (blockIdx.x * 64 >= k.cols) return;
   __shared__ float red[8][64];
   const int w = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.z * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
   float a0 = 0.f, a1 = 0.f;
   if (c < k.cols) {
-    for (int64_t r = w; r < rows; r += 8) {
+#pragma unroll 4
+    for (int64_t r = r0 + w; r < r1; r += 8) {
       const uint32_t u = *reinterpret_cast<const uint32_t*>(k.p + r * k.ld + c);
       a0 += bf16_lo(u); a1 += bf16_hi(u);
     }
@@ -469,20 +472,21 @@ __global__ void colsum_bf16_kernel(const __grid_constant__ ColsumTasks T, int64_
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
-    k.out[blockIdx.x * 64 + threadIdx.x] = s;
+    atomicAdd(k.out + blockIdx.x * 64 + threadIdx.x, s);
   }
 }
 
 // x_emb gradient from S[v*N+q, h] = sum_b [bit_q(b) == v] dh0[b, h]:  g[v, e] = sum_q sum_h S[vN+q, h] Win[h, qE+e]
 __global__ void xemb_grad_kernel(int N, int E, int H, const float* __restrict__ S, const float* __restrict__ in_w,
                                  float* __restrict__ g_xemb) {
-  const int q = blockIdx.x, h0 = blockIdx.y * 64;
+  const int q = blockIdx.x, h0 = blockIdx.y * 16;
   for (int j = threadIdx.x; j < 2 * E; j += blockDim.x) {
     const int v = j / E, e = j - v * E;
     const float* s = S + (int64_t)(v * N + q) * H + h0;
     const float* w = in_w + (int64_t)h0 * (N * E) + q * E + e;
     float acc = 0.f;
-    for (int h = 0; h < 64; ++h) acc = fmaf(s[h], w[(int64_t)h * (N * E)], acc);
+#pragma unroll
+    for (int h = 0; h < 16; ++h) acc = fmaf(s[h], w[(int64_t)h * (N * E)], acc);
     atomicAdd(g_xemb + j, acc);
   }
 }
@@ -859,10 +863,12 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
     }
     add(dh0, H, H, grads + pr.in_b);
     add(dlog, 32, 2 * N, grads + pr.head_b);
-    colsum_bf16_kernel<<<dim3((unsigned)((maxc + 63) / 64), (unsigned)n), 256, 0, s>>>(T, B);
+    const int chunks = (int)((B + 127) / 128 < 16 ? (B + 127) / 128 : 16);
+    const int64_t per = (B + chunks - 1) / chunks;
+    colsum_bf16_kernel<<<dim3((unsigned)((maxc + 63) / 64), (unsigned)n, (unsigned)chunks), 256, 0, s>>>(T, B, per);
     DDQST_LAUNCH_OK();
   }
-  if (var_b) xemb_grad_kernel<<<dim3((unsigned)N, (unsigned)(H / 64)), 128, 0, s>>>(N, E, H, S, params + pr.in_w, grads + pr.x_emb);
+  if (var_b) xemb_grad_kernel<<<dim3((unsigned)N, (unsigned)(H / 16)), 128, 0, s>>>(N, E, H, S, params + pr.in_w, grads + pr.x_emb);
   else in_a_wgrad_kernel<<<(unsigned)((H * N + 127) / 128), 128, 0, s>>>(N, H, S, grads + pr.in_w);
   DDQST_LAUNCH_OK();
   return DDQST_OK;
