@@ -181,33 +181,55 @@ __global__ void __launch_bounds__(256) coeff_table_kernel(const uint32_t* __rest
     int s = j * 32 + lane;
     v[j] = s < dim ? (int)hist[(int64_t)b * dim + s] : 0;
   }
-  const int low = N < 5 ? N : 5;
-  for (int i = 0; i < low; ++i) {
-    const bool upper = (lane >> i) & 1;
-#pragma unroll
-    for (int j = 0; j < E; ++j) {
-      int other = __shfl_xor_sync(0xFFFFFFFFu, v[j], 1 << i);
-      v[j] = upper ? other - v[j] : v[j] + other;
+  uint32_t bx = 0, bz = 0;                               // label-space masks: X-or-Y letters, Y-or-Z letters
+  int rem = b;
+  for (int i = N - 1; i >= 0; --i) { int d = rem % 3; rem /= 3; if (d != 2) bx |= 1u << i; if (d != 0) bz |= 1u << i; }
+  const double sh = (double)shots[b];
+  auto emit = [&](uint32_t m, int val) {
+    if ((int)m < dim && (m & bz) == bz) {
+      uint32_t xl = m & bx, zl = m & bz;
+      if (kron != DDQST_KRON_REVERSED) { xl = __brev(xl) >> (32 - N); zl = __brev(zl) >> (32 - N); }
+      Tc[(int64_t)xl * dim + zl] = sh > 0.0 ? (double)val / sh : 0.0;
     }
-  }
+  };
+  // butterflies over the register index (outcome bits 5 and up)
 #pragma unroll
   for (int bit = 1; bit < E; bit <<= 1) {
 #pragma unroll
     for (int j = 0; j < E; ++j)
       if (!(j & bit)) { int a = v[j], c = v[j | bit]; v[j] = a + c; v[j | bit] = a - c; }
   }
-  uint32_t bx = 0, bz = 0;                               // label-space masks: X-or-Y letters, Y-or-Z letters
-  int rem = b;
-  for (int i = N - 1; i >= 0; --i) { int d = rem % 3; rem /= 3; if (d != 2) bx |= 1u << i; if (d != 0) bz |= 1u << i; }
-  const double sh = (double)shots[b];
+  if constexpr (E == 32) {
+    // N = 10: the five lane-bit stages would be 160 shuffles + selects per warp and make the kernel issue-bound (1.5 TB/s).
+    // Transpose the 32x32 block through shared memory instead (row stride 33: conflict-free both ways) so that lane L holds
+    // outcomes 32 L .. 32 L + 31, and finish with register butterflies.
+    __shared__ int tile[8][32 * 33];
+    int* t = tile[threadIdx.x >> 5];
 #pragma unroll
-  for (int j = 0; j < E; ++j) {
-    uint32_t m = (uint32_t)(j * 32 + lane);
-    if ((int)m < dim && (m & bz) == bz) {
-      uint32_t xl = m & bx, zl = m & bz;
-      if (kron != DDQST_KRON_REVERSED) { xl = __brev(xl) >> (32 - N); zl = __brev(zl) >> (32 - N); }
-      Tc[(int64_t)xl * dim + zl] = sh > 0.0 ? (double)v[j] / sh : 0.0;
+    for (int j = 0; j < 32; ++j) t[j * 33 + lane] = v[j];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = t[lane * 33 + i];
+#pragma unroll
+    for (int bit = 1; bit < 32; bit <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (!(i & bit)) { int a = v[i], c = v[i | bit]; v[i] = a + c; v[i | bit] = a - c; }
     }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) emit((uint32_t)(lane * 32 + i), v[i]);
+  } else {
+    const int low = N < 5 ? N : 5;
+    for (int i = 0; i < low; ++i) {
+      const bool upper = (lane >> i) & 1;
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        int other = __shfl_xor_sync(0xFFFFFFFFu, v[j], 1 << i);
+        v[j] = upper ? other - v[j] : v[j] + other;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < E; ++j) emit((uint32_t)(j * 32 + lane), v[j]);
   }
 }
 

@@ -255,6 +255,43 @@ def test_linear_inversion_larger_sizes_against_oracle(dq, N):
     assert np.allclose(dq.get_metrics(got, N), orc.get_metrics(want, N), atol=1e-5)
 
 
+def test_linear_inversion_n10_paths_agree_and_known_answer(dq):
+    """N = 10 (59 049 bases x 1024 outcomes: the register + shared-memory-transpose Walsh-Hadamard path).  The CPU oracle needs
+    ~1 min here, so the full-size check is (a) a known answer -- exact counts of |0..0> must give rho = |0..0><0..0| -- and
+    (b) the canonical fast path against the library's general slot-table path (oracle-checked up to N = 8) on random counts."""
+    N, dim, nb = 10, 1 << 10, 3 ** 10
+    # (a) |0...0>: a Z letter pins that qubit's outcome bit to 0, X / Y letters leave it uniform; counts exact
+    digits = (np.arange(nb)[:, None] // 3 ** np.arange(N - 1, -1, -1)[None, :]) % 3        # letter of qubit i (0=X,1=Y,2=Z)
+    zmask = ((digits == 2) * (1 << np.arange(N))[None, :]).sum(axis=1)                     # bits that must be 0
+    free = N - (digits == 2).sum(axis=1)
+    s = np.arange(dim)
+    hist = np.where((s[None, :] & zmask[:, None]) == 0, (1 << 22) >> free[:, None], 0).astype(np.int64)   # 2^22 shots per basis, exact
+    assert (hist.sum(axis=1) == hist.sum(axis=1)[0]).all()
+    rho = dq.linear_inversion_raw(torch.from_numpy(hist.astype(np.int32)).cuda(), N).cpu().numpy()
+    want = np.zeros((dim, dim), dtype=complex)
+    want[0, 0] = 1.0
+    assert np.abs(rho - want).max() < 1e-12
+    # (b) random counts: fast path (sel = NULL) vs general path with the explicit canonical slot table
+    lib = dq._lib.load()
+    rng = np.random.default_rng(3)
+    h = torch.from_numpy(rng.integers(0, 1000, size=(nb, dim)).astype(np.int32)).cuda()
+    shots = h.to(torch.int64).sum(dim=1)
+    p = np.arange(4 ** N)
+    letters = (p[:, None] // 4 ** np.arange(N - 1, -1, -1)[None, :]) % 4                   # 0=I,1=X,2=Y,3=Z per qubit
+    sel = (np.where(letters == 0, 0, letters - 1) * 3 ** np.arange(N - 1, -1, -1)[None, :]).sum(axis=1).astype(np.int32)
+    sel[0] = -2
+    sel_d = torch.from_numpy(sel).cuda()
+    out = [torch.empty(dim, dim, dtype=torch.complex128, device="cuda") for _ in range(2)]
+    ws = torch.empty(nb * dim * 4 + 8 * dim * dim + 256, dtype=torch.uint8, device="cuda")
+    P, S = dq._lib.ptr, dq._lib.stream_ptr
+    hu = h.view(torch.uint32)
+    dq._lib.check(lib.ddqst_linear_inversion(P(hu), P(shots), nb, N, None, 0, P(out[0]), P(ws), ws.numel(), S()))
+    dq._lib.check(lib.ddqst_linear_inversion(P(hu), P(shots), nb, N, P(sel_d), 0, P(out[1]), P(ws), ws.numel(), S()))
+    a, b = out[0].cpu().numpy(), out[1].cpu().numpy()
+    assert np.abs(a - b).max() < 1e-12
+    assert np.abs(a - a.conj().T).max() < 1e-12 and abs(np.trace(a).real - 1) < 1e-12
+
+
 def test_linear_inversion_dict_order_and_missing_bases(dq):
     """First-compatible-basis rule (RQC/reconstruct.py:32-38) for a shuffled / incomplete dict; 0.0 when none fits."""
     rng = np.random.default_rng(2)
