@@ -221,7 +221,7 @@ def run_native(args):
     assert int(hist_host.sum()) == units_per_step
 
     # ---------------- recon + fidelity milliseconds (rank 0) ----------------
-    recon = None
+    recon, train = None, None
     if rank == 0:
         # synthetic random-circuit state measured in all 3^8 bases with 10^6 shots each, generated on the
         # device by the native generator (csrc/synth.cu): brick-wall random circuit, Born sampling from the Philox stream
@@ -262,8 +262,8 @@ def run_native(args):
             tg.replay()
         b.record()
         torch.cuda.synchronize()
-        recon["train_step_ms"] = a.elapsed_time(b) / 20
-        recon["train_step_what"] = "C4 model, batch 1024, tcgen05 bf16 fwd+bwd+Adam, CUDA-graph replay"
+        train = {"ms": a.elapsed_time(b) / 20, "samples_per_s": 1024 / (a.elapsed_time(b) / 20) * 1e3,
+                 "what": "C4 model, batch 1024: t draw + noising + tcgen05 bf16 fwd/bwd + Adam, CUDA-graph replay"}
         assert lib.ddqst_debug_tc_status() == 0, "tcgen05 pipeline timed out (train step)"
 
     # ---------------- roofline of the dominant kernel ----------------
@@ -295,7 +295,7 @@ def run_native(args):
             "e2e": {"value": e2e_value, "unit": "bitstrings/s", "h2d_bytes_per_step": 4 * bps,
                     "d2h_bytes_per_step": bps * shots + bps * (4 << N)},
             "gpu_launches": args.steps,
-            "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu, "recon_fidelity": recon,
+            "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu, "recon_fidelity": recon, "train_step": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
