@@ -370,14 +370,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   gemm_tile<BN, EPI>(&mapA, &mapB, G, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
 }
 
-// Several independent TE_STORE problems (the weight-gradient GEMMs of one step) in ONE launch: CTA i belongs to the group
+// Several independent problems (the weight-gradient GEMMs of one step and the FiLM data gradient) in ONE launch: CTA i belongs to the group
 // whose [start, start + tiles) range contains i.  Saves the launch + drain of four small kernels per step.
-constexpr int kGtMaxGroup = 5;
+constexpr int kGtMaxGroup = 6;
 struct TcGroup {
   CUtensorMap mapA[kGtMaxGroup], mapB[kGtMaxGroup];
   TcGemm g[kGtMaxGroup];
   int start[kGtMaxGroup + 1];
   int tiles_m[kGtMaxGroup], tiles_n[kGtMaxGroup];
+  int epi[kGtMaxGroup];            // TE_STORE or TE_DCOND
   int n;
 };
 template <int BN>
@@ -389,7 +390,8 @@ __global__ void __launch_bounds__(kGtThreads) gemm_tc_group_kernel(const __grid_
     if (k < P.n && lin >= P.start[k]) i = k;
   const int local = lin - P.start[i];
   const int tm = P.tiles_m[i], tn = P.tiles_n[i];
-  gemm_tile<BN, TE_STORE>(&P.mapA[i], &P.mapB[i], P.g[i], local % tm, (local / tm) % tn, local / (tm * tn));
+  if (P.epi[i] == TE_DCOND) gemm_tile<BN, TE_DCOND>(&P.mapA[i], &P.mapB[i], P.g[i], local % tm, (local / tm) % tn, local / (tm * tn));
+  else gemm_tile<BN, TE_STORE>(&P.mapA[i], &P.mapB[i], P.g[i], local % tm, (local / tm) % tn, local / (tm * tn));
 }
 
 // ------------------------------------------------------------------------------------ small CUDA-core kernels
@@ -624,8 +626,9 @@ static int launch_gemm_bn(const HostOperand& A, const HostOperand& B, TcGemm g, 
 struct GroupBuilder {
   TcGroup grp{};
   int total = 0;
-  int add(const HostOperand& A, const HostOperand& B, TcGemm g, int zcount) {
+  int add(const HostOperand& A, const HostOperand& B, TcGemm g, int zcount, int epi = TE_STORE) {
     const int i = grp.n;
+    grp.epi[i] = epi;
     if (i >= kGtMaxGroup) { set_error("too many problems in one grouped GEMM launch"); return DDQST_EINVAL_SHAPE; }
     if (A.mn_major) DDQST_TRY(make_map3(&grp.mapA[i], A.base, A.mn, A.k, A.batch, A.ld, A.batch_stride, 64));
     else DDQST_TRY(make_map3(&grp.mapA[i], A.base, A.k, A.mn, A.batch, A.ld, A.batch_stride, 128));
@@ -806,18 +809,18 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
       DDQST_TRY(launch_gemm<TE_BW1>(op_k(dz + 2 * l * BH, B, H, H), op_mn(shadow + pr.w1[l], H, H, H), g, 1, s));
     }
   }
-  {  // dcond = sum_l dgb_l . Wfilm_l, scattered into the time / basis embedding gradients; the sum over blocks is a
-     // split-K over z (one block per z): the epilogue accumulates with atomics anyway
-    TcGemm g = base_gemm((int)B, 2 * E, 2 * H);
-    g.o0 = grads + pr.time_emb; g.o1 = grads + pr.basis_emb; g.i0 = t; g.i1 = basis;
-    HostOperand A{dgb, 0, B, 2 * H, L, 2 * H, BG, 0, 1};
-    HostOperand Bo{shadow + pr.film_w[0], 1, 2 * E, 2 * H, L, 2 * E, blk_stride > 0 ? blk_stride : (int64_t)2 * H * 2 * E, 0, 1};
-    DDQST_TRY(launch_gemm<TE_DCOND>(A, Bo, g, L, s));
-  }
   // ------------------------------------------------------------------ backward: weight gradients (dY^T . X over the batch)
-  // five independent problems, one grouped launch
+  // six independent problems (five weight gradients + the FiLM data gradient), one grouped launch
   {
     GroupBuilder grp;
+    {  // dcond = sum_l dgb_l . Wfilm_l, scattered into the time / basis embedding gradients; the sum over blocks is a
+       // split-K over z (one block per z): the epilogue accumulates with atomics anyway
+      TcGemm g = base_gemm((int)B, 2 * E, 2 * H);
+      g.o0 = grads + pr.time_emb; g.o1 = grads + pr.basis_emb; g.i0 = t; g.i1 = basis;
+      HostOperand A{dgb, 0, B, 2 * H, L, 2 * H, BG, 0, 1};
+      HostOperand Bo{shadow + pr.film_w[0], 1, 2 * E, 2 * H, L, 2 * E, blk_stride > 0 ? blk_stride : (int64_t)2 * H * 2 * E, 0, 1};
+      DDQST_TRY(grp.add(A, Bo, g, L, TE_DCOND));
+    }
     {  // W1_l, W2_l for every block: z = 2l (dz1_l, a_l), 2l+1 (dz2_l, u_l)
       TcGemm g = base_gemm(H, H, (int)B);
       g.o0 = grads;
