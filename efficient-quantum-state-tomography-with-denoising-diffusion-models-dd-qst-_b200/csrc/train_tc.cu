@@ -673,7 +673,9 @@ static int launch_gemm(const HostOperand& A, const HostOperand& B, const TcGemm&
   const int64_t tiles128 = (int64_t)((g.M + 127) / 128) * ((g.N + 127) / 128) * zcount;
   const bool fused = EPI != TE_STORE && EPI != TE_DCOND && EPI != TE_HEAD;
   const bool can128 = !fused || g.N % 128 == 0;
-  if (can128 && EPI != TE_HEAD && tiles128 >= 96) return launch_gemm_bn<128, EPI>(A, B, g, zcount, s);
+  static int thr = -1;
+  if (thr < 0) { const char* e = getenv("DDQST_TC_BN128_TILES"); thr = e ? atoi(e) : 96; }      // tuning knob: min 128x128 tiles for BN = 128
+  if (can128 && EPI != TE_HEAD && tiles128 >= thr) return launch_gemm_bn<128, EPI>(A, B, g, zcount, s);
   return launch_gemm_bn<64, EPI>(A, B, g, zcount, s);
 }
 
