@@ -851,6 +851,206 @@ __global__ void __launch_bounds__(kJcThreads) jacobi_ring_kernel(double2* __rest
   jc_cluster_barrier();                               // nobody exits while a peer could still write into its inbox
 }
 
+// ---- odd-even ordering: the same register-resident, st.async-linked scheme with HALF the traffic of the ring.  Columns sit on
+// a line of n positions; even steps rotate the pairs (0,1),(2,3),.., odd steps (1,2),(3,4),.., and after every rotation the two
+// columns swap positions.  After n steps every pair has met exactly once (the order is reversed, which is irrelevant here).
+// Warp k always works on two adjacent positions: after an even step it passes its lower column to warp k-1 and receives warp
+// k+1's lower column; after an odd step it passes its upper column to warp k+1 and receives warp k-1's upper column -- ONE
+// column out and one in per step (the ring moves two).  Position 0 is parked by warp 0 during odd steps, position n-1 idles
+// in warp h-1.  Inbox / mbarrier protocol as in the ring: parity-1 inboxes are only ever written by the right neighbour,
+// parity-0 inboxes by the left one, and a neighbour cannot run ahead by more than one step because it needs this warp's output.
+template <int EPL>
+__global__ void __launch_bounds__(kJcThreads) jacobi_oddeven_kernel(double2* __restrict__ GT, int n, int max_sweeps, double tol,
+                                                                   JacobiCtl* ctl) {
+  extern __shared__ __align__(16) uint8_t jr_smem[];
+  constexpr int COLB = EPL * 32 * 16;
+  constexpr int WPC = kJcThreads / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int h = n / 2, k = (int)crank * WPC + warp;
+  const bool active = k < h;
+  const uint32_t smem0 = smem_u32(jr_smem);
+  const uint32_t bars0 = smem0 + WPC * 3 * COLB;
+  // per warp: inbox[0] (from the left, read before even steps), inbox[1] (from the right, read before odd steps), park slot
+  auto inbox = [&](int w, int par) { return smem0 + (uint32_t)((w * 3 + par) * COLB); };
+  auto bar = [&](int w, int par) { return bars0 + (uint32_t)((w * 2 + par) * 8); };
+  uint8_t* park = jr_smem + (warp * 3 + 2) * COLB;
+  const uint32_t colbytes = (uint32_t)n * 16u;
+  const bool recv_right = active && k <= h - 2;       // after even steps: a column arrives from warp k+1 (barrier 1)
+  const bool recv_left = active && k >= 1;            // after odd steps: a column arrives from warp k-1 (barrier 0)
+  if (lane == 0) {
+    mbar_init(bar(warp, 0), 1); mbar_init(bar(warp, 1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (recv_left) mbar_expect_tx(bar(warp, 0), colbytes);
+    if (recv_right) mbar_expect_tx(bar(warp, 1), colbytes);
+  }
+  double2 a[EPL], b[EPL];                              // lower / upper position of this warp's current pair
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int i = lane + 32 * e;
+    const bool ok = active && i < n;
+    a[e] = ok ? GT[(int64_t)(2 * k) * n + i] : make_double2(0.0, 0.0);
+    b[e] = ok ? GT[(int64_t)(2 * k + 1) * n + i] : make_double2(0.0, 0.0);
+  }
+  uint32_t left_addr = 0, left_bar = 0, right_addr = 0, right_bar = 0;
+  if (recv_left) {                                     // my left neighbour k-1 exists: after even steps I send into ITS inbox[1]
+    left_addr = jr_mapa(inbox((k - 1) % WPC, 1), (uint32_t)((k - 1) / WPC));
+    left_bar = jr_mapa(bar((k - 1) % WPC, 1), (uint32_t)((k - 1) / WPC));
+  }
+  if (recv_right) {                                    // my right neighbour k+1 exists: after odd steps I send into ITS inbox[0]
+    right_addr = jr_mapa(inbox((k + 1) % WPC, 0), (uint32_t)((k + 1) / WPC));
+    right_bar = jr_mapa(bar((k + 1) % WPC, 0), (uint32_t)((k + 1) / WPC));
+  }
+  __syncwarp();
+  jc_cluster_barrier();
+  int sweep = 0;
+  uint32_t g = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    int rot = 0;
+    float worst = 0.f;
+    if (active) {
+      for (int step = 0; step < n; ++step, ++g) {
+        const bool odd = (g & 1u) != 0u;
+        if (!odd || k <= h - 2) {                      // in odd steps the last warp only holds the idle position n-1
+          double sa = 0.0, sb = 0.0, gr = 0.0, gi = 0.0;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) {
+            sa += a[e].x * a[e].x + a[e].y * a[e].y;
+            sb += b[e].x * b[e].x + b[e].y * b[e].y;
+            gr += a[e].x * b[e].x + a[e].y * b[e].y;     // conj(a)*b
+            gi += a[e].x * b[e].y - a[e].y * b[e].x;
+          }
+          sa = warp_sum(sa); sb = warp_sum(sb); gr = warp_sum(gr); gi = warp_sum(gi);
+          sa = __shfl_sync(0xFFFFFFFFu, sa, 0); sb = __shfl_sync(0xFFFFFFFFu, sb, 0);
+          gr = __shfl_sync(0xFFFFFFFFu, gr, 0); gi = __shfl_sync(0xFFFFFFFFu, gi, 0);
+          const double g2 = gr * gr + gi * gi;
+          worst = fmaxf(worst, (float)(g2 / (sa * sb)));
+          double c = 1.0, s = 0.0, pr = 1.0, pi = 0.0;
+          const bool on = g2 > tol * tol * sa * sb && g2 > 1e-60;
+          if (on) {
+            if (g2 > 1e-30 && g2 < 1e30) {
+              const double inv_g = jr_rsqrt(g2);
+              const double zeta = 0.5 * (sb - sa) * inv_g, az = fabs(zeta);
+              const double az2 = fma(az, az, 1.0);
+              const double at = az < 1e7 ? jr_rcp(az + az2 * jr_rsqrt(az2)) : 0.5 * jr_rcp(az);
+              const double t = zeta >= 0.0 ? at : -at;
+              c = jr_rsqrt(fma(t, t, 1.0)); s = c * t;
+              pr = gr * inv_g; pi = -gi * inv_g;
+            } else {
+              const double gabs = sqrt(g2);
+              const double zeta = (sb - sa) / (2.0 * gabs);
+              const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+              c = 1.0 / sqrt(1.0 + t * t); s = c * t;
+              pr = gr / gabs; pi = -gi / gabs;
+            }
+            ++rot;
+          }
+          // rotate and swap positions in one go: new lower = rotated upper, new upper = rotated lower
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) {
+            const double2 a0 = a[e], b0 = b[e];
+            if (on) {
+              const double2 br = make_double2(b0.x * pr - b0.y * pi, b0.x * pi + b0.y * pr);
+              a[e] = make_double2(s * a0.x + c * br.x, s * a0.y + c * br.y);       // rotated upper -> lower position
+              b[e] = make_double2(c * a0.x - s * br.x, c * a0.y - s * br.y);       // rotated lower -> upper position
+            } else {
+              a[e] = b0; b[e] = a0;
+            }
+          }
+        }
+        if (!odd) {
+          // even -> odd: lower position goes left (or is parked by warp 0); my upper becomes my lower; new upper from the right
+          if (k >= 1) {
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) { const int i = lane + 32 * e; if (i < n) jr_send(left_addr + (uint32_t)i * 16u, a[e], left_bar); }
+          } else {
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) { const int i = lane + 32 * e; if (i < n) *reinterpret_cast<double2*>(park + i * 16) = a[e]; }
+          }
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) a[e] = b[e];
+          if (recv_right) {
+            mbar_wait(bar(warp, 1), (g >> 1) & 1u, 62);
+            const uint8_t* in = jr_smem + (warp * 3 + 1) * COLB;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) { const int i = lane + 32 * e; if (i < n) b[e] = *reinterpret_cast<const double2*>(in + i * 16); }
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(bar(warp, 1), colbytes);
+          }
+        } else {
+          // odd -> even: upper position goes right; my lower becomes my upper; new lower from the left (warp 0: the parked column)
+          if (k <= h - 2) {
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) { const int i = lane + 32 * e; if (i < n) jr_send(right_addr + (uint32_t)i * 16u, b[e], right_bar); }
+          }
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) b[e] = a[e];
+          if (recv_left) {
+            mbar_wait(bar(warp, 0), (g >> 1) & 1u, 63);
+            const uint8_t* in = jr_smem + (warp * 3 + 0) * COLB;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) { const int i = lane + 32 * e; if (i < n) a[e] = *reinterpret_cast<const double2*>(in + i * 16); }
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(bar(warp, 0), colbytes);
+          } else {
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) { const int i = lane + 32 * e; if (i < n) a[e] = *reinterpret_cast<const double2*>(park + i * 16); }
+          }
+        }
+      }
+      if (lane == 0 && rot > 0) atomicAdd(&ctl->rotations[sweep], rot);
+      if (lane == 0 && sweep < 48) atomicMax(&ctl->max_ratio2[sweep], __float_as_uint(worst));
+    }
+    jc_cluster_barrier();
+    const int total = __ldcg(&ctl->rotations[sweep]);
+    if (total == 0) { ++sweep; break; }
+    if (sweep < 48 && __uint_as_float(__ldcg(&ctl->max_ratio2[sweep])) < 1e-14f) { ++sweep; break; }
+  }
+  if (active) {                                       // after whole sweeps warp k holds positions 2k, 2k+1 again
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int i = lane + 32 * e;
+      if (i < n) { GT[(int64_t)(2 * k) * n + i] = a[e]; GT[(int64_t)(2 * k + 1) * n + i] = b[e]; }
+    }
+  }
+  if (k == 0 && lane == 0) ctl->sweeps_done = sweep;
+  jc_cluster_barrier();
+}
+
+template <int EPL>
+static int launch_jacobi_oddeven(double2* GT, int n, int max_sweeps, double tol, JacobiCtl* ctl, cudaStream_t s, bool* launched) {
+  constexpr int smem = (kJcThreads / 32) * 3 * EPL * 32 * 16 + 256;
+  *launched = false;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DDQST_CUDA_OK(cudaFuncSetAttribute(jacobi_oddeven_kernel<EPL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    DDQST_CUDA_OK(cudaFuncSetAttribute(jacobi_oddeven_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  int csize = (n / 2 + kJcThreads / 32 - 1) / (kJcThreads / 32);
+  if (csize < 1) csize = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)csize);
+  cfg.blockDim = dim3(kJcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int fits = 0;
+  if (cudaOccupancyMaxActiveClusters(&fits, jacobi_oddeven_kernel<EPL>, &cfg) != cudaSuccess || fits < 1) {
+    (void)cudaGetLastError();
+    return DDQST_OK;
+  }
+  DDQST_CUDA_OK(cudaLaunchKernelEx(&cfg, jacobi_oddeven_kernel<EPL>, GT, n, max_sweeps, tol, ctl));
+  *launched = true;
+  return DDQST_OK;
+}
+
 template <int EPL>
 static int launch_jacobi_ring(double2* GT, int n, int max_sweeps, double tol, JacobiCtl* ctl, cudaStream_t s, bool* launched) {
   constexpr int smem = (kJcThreads / 32) * 4 * EPL * 32 * 16 + 256;
@@ -927,7 +1127,16 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
   bool ring_done = false;
   const char* ring_env = getenv("DDQST_JACOBI_RING");          // DDQST_JACOBI_RING=0 keeps the L2-resident kernel (debugging aid)
   if (ring_env == nullptr || ring_env[0] != '0') {
-    if (n <= 256) {
+    if (n <= 256 && (ring_env == nullptr || ring_env[0] != '1')) {      // DDQST_JACOBI_RING=1 forces the two-column ring
+      const int epl = n <= 32 ? 1 : n / 32;
+      switch (epl) {
+        case 1: DDQST_TRY(launch_jacobi_oddeven<1>(GT, n, max_sweeps, tol, ctl, s, &ring_done)); break;
+        case 2: DDQST_TRY(launch_jacobi_oddeven<2>(GT, n, max_sweeps, tol, ctl, s, &ring_done)); break;
+        case 4: DDQST_TRY(launch_jacobi_oddeven<4>(GT, n, max_sweeps, tol, ctl, s, &ring_done)); break;
+        default: DDQST_TRY(launch_jacobi_oddeven<8>(GT, n, max_sweeps, tol, ctl, s, &ring_done)); break;
+      }
+    }
+    if (!ring_done && n <= 256) {
       const int epl = n <= 32 ? 1 : n / 32;
       switch (epl) {
         case 1: DDQST_TRY(launch_jacobi_ring<1>(GT, n, max_sweeps, tol, ctl, s, &ring_done)); break;
