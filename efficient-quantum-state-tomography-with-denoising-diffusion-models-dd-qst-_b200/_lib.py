@@ -73,6 +73,8 @@ SIGNATURES = {
     "ddqst_selftest_philox": (C.c_int, [_P, _I64, _P, _P]),
     "ddqst_selftest_umma": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
     "ddqst_selftest_umma2": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
+    "ddqst_selftest_gemm_tc_dbg": (C.c_int, [_P, _P, C.c_int, C.c_int, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "ddqst_debug_tc_trace": (C.c_int, [_P, _I32]),
     "ddqst_debug_tc_status": (C.c_int, []),
 }
 

@@ -261,6 +261,14 @@ int ddqst_selftest_umma2(const float* a, const uint16_t* w_bf16, int32_t m_pairs
  * (a_mn == 0: A is [m,k] row-major, else [k,m]; b_mn == 0: B is [n,k] row-major, else [k,n]); n % 4 == 0 */
 int ddqst_selftest_gemm_tc(const uint16_t* a, const uint16_t* b, int a_mn, int b_mn, int32_t m, int32_t n, int32_t k,
                            int32_t batch, float* c, void* stream);
+/* debugging aids of the training GEMM kernel (benchmarks/gemm_tc_stamps.py, benchmarks/train_trace.py):
+ * selftest_gemm_tc_dbg additionally writes 8 clock64 stamps of CTA (0,0,0) to dbg (device int64[8]);
+ * debug_tc_trace registers (or, with NULL, clears) a device buffer of 4*cap int64: GEMM launch i of the following
+ * ddqst_train_forward_backward_tc calls writes its %globaltimer entry / dependency-release / epilogue-done stamps and its
+ * epilogue id to buf[4*i .. 4*i+3] (process-wide state, not thread-safe: debugging only). */
+int ddqst_selftest_gemm_tc_dbg(const uint16_t* a, const uint16_t* b, int a_mn, int b_mn, int32_t m, int32_t n, int32_t k,
+                               int32_t batch, float* c, long long* dbg, void* stream);
+int ddqst_debug_tc_trace(long long* buf, int32_t cap);
 /* synchronises the device; returns the first pipeline-timeout code a tcgen05 kernel recorded (0 = none) */
 int ddqst_debug_tc_status(void);
 
