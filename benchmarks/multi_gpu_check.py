@@ -56,8 +56,8 @@ def main():
     lo, hi = dq.shard_range(B, rank, world)
     for step in range(3):
         # single process: the whole batch through a private (size-1) group so no exchange happens
-        ref_loss = ref_diff.train_step(x0.to(dev), basis.to(dev), ref_opt, process_group=self_group)
-        dp_loss = dp_diff.train_step(x0[lo:hi].to(dev), basis[lo:hi].to(dev), dp_opt, row_offset=lo)
+        ref_loss = ref_diff.train_step(x0.to(dev), basis.to(dev), ref_opt)
+        dp_loss = dp_diff.train_step(x0[lo:hi].to(dev), basis[lo:hi].to(dev), dp_opt, row_offset=lo, data_parallel=True)
     diffs = [(a - b).abs().max().item() for a, b in zip(ref.state_dict().values(), model.state_dict().values())]
     out["dp_train_max_param_diff"] = max(diffs)
     ok &= max(diffs) < 1e-5

@@ -91,10 +91,14 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if not os.path.exists(path):
-        if not build_if_missing:
-            raise RuntimeError(f"{path} is missing: run `python __graft_entry__.py` / build() first (no CPU fallback)")
-        _build.build()
+    if build_if_missing and _build.have_nvcc():
+        _build.build()                   # incremental (content hash of csrc/ + include/ + flags): a stale .so is rebuilt
+    elif not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing and nvcc is not available: run `python __graft_entry__.py` / build() "
+                           "where nvcc exists (no CPU fallback)")
+    elif not _build.stamp_matches():
+        raise RuntimeError(f"{path} was built from different sources than csrc/ + include/ddqst.h now hold and nvcc is "
+                           "not available to rebuild it")
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
@@ -117,6 +121,30 @@ def ptr(t: torch.Tensor | None):
     if not t.is_contiguous():
         raise RuntimeError("libddqst needs contiguous tensors")
     return C.c_void_p(t.data_ptr())
+
+
+def check_index(idx, hi: int, what: str, lo: int = 0) -> None:
+    """Raise IndexError unless every element of ``idx`` (tensor, list or int) lies in [lo, hi).
+
+    The kernels index their embedding / FiLM / schedule tables with these values unchecked (include/ddqst.h,
+    "index contract"), as ``nn.Embedding`` and ``Q_bar[t]`` raise IndexError in the reference (RQC/model.py:59-61,
+    RQC/diffusion.py:48).  One ``aminmax`` (a device sync for CUDA tensors); callers inside a CUDA-graph capture
+    skip it and own the contract."""
+    if torch.is_tensor(idx):
+        if idx.numel() == 0:
+            return
+        mn, mx = (int(v) for v in torch.aminmax(idx))
+    else:
+        seq = [int(idx)] if isinstance(idx, int) else [int(v) for v in idx]
+        if not seq:
+            return
+        mn, mx = min(seq), max(seq)
+    if mn < lo or mx >= hi:
+        raise IndexError(f"{what} out of range: values span [{mn}, {mx}], valid range is [{lo}, {hi})")
+
+
+def capturing() -> bool:
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
 
 
 def stream_ptr():

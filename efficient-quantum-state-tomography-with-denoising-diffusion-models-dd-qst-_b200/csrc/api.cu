@@ -157,7 +157,7 @@ using namespace ddqst;
 extern "C" {
 
 const char* ddqst_last_error(void) { return g_err; }
-int ddqst_version(void) { return 100; }
+int ddqst_version(void) { return 200; }
 
 int64_t ddqst_param_count(const ddqst_dims* d, int64_t* offsets_out) {
   ParamLayout p;

@@ -151,8 +151,9 @@ __global__ void __launch_bounds__(128) histogram_private_kernel(const T* __restr
       const int64_t nxt = cur + DEPTH * stride;
       if (nxt < nvec) buf[d] = load16(nxt);
       consume(w);
-      if (++since_fold == 65535 / VEC) {                // a private counter cannot have exceeded 65535 yet
-        // warp-uniform trip counts are not guaranteed at the tail, so only fold when the whole warp is here
+      if (++since_fold >= 65535 / VEC - DEPTH) {        // a private counter cannot have exceeded 65535 - DEPTH*VEC yet
+        // warp-uniform trip counts are not guaranteed at the tail, so only fold when the whole warp is here; a skipped
+        // fold is retried on the next vector (>=), and at most DEPTH more vectors follow a ragged tail
         if (__activemask() == 0xFFFFFFFFu) { fold(); since_fold = 0; }
       }
     }
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(256) coeff_table_kernel(const uint32_t* __rest
     if ((int)m < dim && (m & bz) == bz) {
       uint32_t xl = m & bx, zl = m & bz;
       if (kron != DDQST_KRON_REVERSED) { xl = __brev(xl) >> (32 - N); zl = __brev(zl) >> (32 - N); }
-      Tc[(int64_t)xl * dim + zl] = sh > 0.0 ? (double)val / sh : 0.0;
+      Tc[(int64_t)xl * dim + zl] = (double)val / sh;      // zero-shot basis: 0/0 = NaN, as np.mean([]) in RQC/reconstruct.py:44
     }
   };
   // butterflies over the register index (outcome bits 5 and up)
@@ -310,7 +311,7 @@ __global__ void rho_assemble_kernel(const int32_t* __restrict__ W, const int64_t
       }
     }
     if (slot == -2) coeff = 1.0;
-    else if (slot < 0 || slot >= n_slots || shots[slot] <= 0) coeff = 0.0;
+    else if (slot < 0 || slot >= n_slots) coeff = 0.0;     // no compatible basis: RQC/reconstruct.py:46 (a zero-shot one gives 0/0 = NaN below)
     else coeff = (double)W[(int64_t)slot * dim + support] / (double)shots[slot];
     int ny = __popc(xm & (uint32_t)z) & 3;   // (-i)^ny
     double2 v;

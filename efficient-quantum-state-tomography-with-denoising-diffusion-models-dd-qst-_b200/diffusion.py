@@ -150,6 +150,7 @@ class DiscreteDiffusion:
         if stream_id is None:
             stream_id = self._q_calls
             self._q_calls += 1
+        _lib.check_index(t, self.num_timesteps + 1, "t")          # Q_bar[t] raises IndexError in the reference
         x0p = pack_bits(x_0.to(self.device), N)
         t32 = t.to(self.device).to(torch.int32).contiguous()
         xtp = torch.empty_like(x0p)
@@ -167,6 +168,8 @@ class DiscreteDiffusion:
         lib = _lib.load()
         m = self.model
         N = m.num_qubits
+        if not _lib.capturing():
+            _lib.check_index(bases, m.num_bases, "basis index")       # the FiLM table Tb has num_bases rows
         if torch.is_tensor(bases):
             ids = bases.to(device=self.device, dtype=torch.int32).contiguous()
         else:
@@ -198,6 +201,7 @@ class DiscreteDiffusion:
         nb = basis_ids_host.numel()
         if basis_ids_host.dtype != torch.int32 or basis_ids_host.is_cuda:
             raise ValueError("basis_ids_host must be a host int32 tensor")
+        _lib.check_index(basis_ids_host, m.num_bases, "basis index")
         need = 4 * nb + (nb << N) * 4 + nb * n_shots * (1 if N <= 8 else 2) + 4096 + \
             lib.ddqst_workspace_bytes(_lib.OP_SAMPLE, C.byref(m.dims), nb * n_shots, self._prec())
         scratch = _lib.workspace.get(need, self.device)
@@ -242,14 +246,33 @@ class DiscreteDiffusion:
               and m.num_qubits <= 15 and m.num_blocks <= 16)
         return "bf16" if ok else "fp32"
 
-    def train_step(self, x_0: torch.Tensor, basis: torch.Tensor, optimizer: NativeAdam, row_offset: int = 0,
-                   process_group=None, precision: str | None = None):
+    def _dp(self, process_group, data_parallel):
+        """-> (world, rank) of the data-parallel group, (1, 0) unless the caller asked for data parallelism.  An initialised
+        default process group alone does NOT turn the all-reduce on: a step run by a subset of the ranks would block forever."""
+        if process_group is None and not data_parallel:
+            return 1, 0
+        if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            raise RuntimeError("data-parallel train_step needs an initialised torch.distributed process group")
+        return torch.distributed.get_world_size(process_group), torch.distributed.get_rank(process_group)
+
+    def train_step(self, x_0: torch.Tensor, basis: torch.Tensor, optimizer: NativeAdam, row_offset: int | None = None,
+                   process_group=None, precision: str | None = None, data_parallel: bool = False, validate: bool = True):
         """One step of RQC/main.py:105-115 fused: t ~ U{1..T}, x_t = q_sample(x_0, t), logits, mean cross-entropy,
-        backward, (all-reduce of the flat gradient when a process group is given,) Adam.  Returns the loss (device scalar).
-        ``precision`` 'bf16' runs every GEMM on the tensor cores, 'fp32' the exact CUDA-core path (default: train_precision())."""
+        backward, Adam.  Returns the loss (device scalar; the local batch's mean).
+        ``precision`` 'bf16' runs every GEMM on the tensor cores, 'fp32' the exact CUDA-core path (default: train_precision()).
+        Data parallel (``process_group=...`` or ``data_parallel=True`` for the default group; EVERY rank of the group must
+        call): the flat gradient is summed by one NCCL all-reduce and scaled by 1/world inside the Adam kernel;
+        ``row_offset`` (the global row index of local row 0, which keys the t / noise draws) then defaults to rank * B so
+        the ranks draw disjoint streams.  ``validate`` range-checks ``basis`` (one device sync; IndexError as nn.Embedding
+        raises in the reference) -- skipped during CUDA-graph capture."""
         self._require_cuda()
+        if validate and not _lib.capturing():
+            _lib.check_index(basis, self.model.num_bases, "basis")
+        world, rank = self._dp(process_group, data_parallel)
+        if row_offset is None:
+            row_offset = rank * x_0.shape[0] if world > 1 else 0
         if (precision or self.train_precision()) == "bf16":
-            return self._train_step_tc(x_0, basis, optimizer, row_offset, process_group)
+            return self._train_step_tc(x_0, basis, optimizer, row_offset, process_group, world)
         lib = _lib.load()
         m = self.model
         N = m.num_qubits
@@ -268,9 +291,6 @@ class DiscreteDiffusion:
             self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         nbytes = lib.ddqst_workspace_bytes(_lib.OP_TRAIN, C.byref(m.dims), B, _lib.PRECISION_FP32)
         ws = _lib.workspace.get(nbytes, self.device)
-        world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            world = torch.distributed.get_world_size(process_group)
         _lib.check(lib.ddqst_train_forward_backward(C.byref(m.dims), _lib.ptr(m.flat_params), _lib.ptr(xtp), _lib.ptr(x0p),
                                                     _lib.ptr(t32), _lib.ptr(b32), B, 1.0, _lib.ptr(grads), _lib.ptr(self._loss),
                                                     _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
@@ -281,7 +301,7 @@ class DiscreteDiffusion:
         optimizer.step(grads, grad_scale=scale)
         return self._loss
 
-    def _train_step_tc(self, x_0, basis, optimizer: NativeAdam, row_offset: int = 0, process_group=None):
+    def _train_step_tc(self, x_0, basis, optimizer: NativeAdam, row_offset: int = 0, process_group=None, world: int = 1):
         """Tensor-core form of train_step.  Nothing here depends on host-side counters (the step count that keys the
         noising stream and Adam's bias correction lives in ``optimizer.step_dev``), so the call can be captured in a
         CUDA graph (see ``make_train_graph``)."""
@@ -307,34 +327,39 @@ class DiscreteDiffusion:
         _lib.check(lib.ddqst_train_forward_backward_tc(C.byref(m.dims), _lib.ptr(m.flat_params), _lib.ptr(shadow), _lib.ptr(st["xt"]),
                                                        _lib.ptr(x0p), _lib.ptr(st["t"]), _lib.ptr(b32), B, 1.0, _lib.ptr(st["grads"]),
                                                        _lib.ptr(st["loss"]), _lib.ptr(st["ws"]), st["ws"].numel(), _lib.stream_ptr()))
-        world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            world = torch.distributed.get_world_size(process_group)
         scale = 1.0
         if world > 1:
-            torch.distributed.all_reduce(st["grads"], group=process_group)
+            torch.distributed.all_reduce(st["grads"], group=process_group)       # NCCL; capturable in a CUDA graph
             scale = 1.0 / world
         optimizer.step_device(st["grads"], grad_scale=scale, shadow=shadow)
         self._train_steps += 1
         return st["loss"]
 
-    def make_train_graph(self, x0_packed: torch.Tensor, basis_i32: torch.Tensor, optimizer: NativeAdam, row_offset: int = 0):
+    def make_train_graph(self, x0_packed: torch.Tensor, basis_i32: torch.Tensor, optimizer: NativeAdam,
+                         row_offset: int | None = None, process_group=None, data_parallel: bool = False):
         """Capture one tensor-core training step on the STATIC device buffers ``x0_packed`` (uint16[B]) and ``basis_i32``
         (int32[B]) in a CUDA graph.  Returns a ``TrainGraph``: refill the two buffers, call ``.replay()``.
-        Single-GPU form (an all-reduce would have to be captured with it)."""
+        Data parallel (``process_group`` / ``data_parallel=True``, every rank must call and replay in lockstep): the NCCL
+        gradient all-reduce is captured inside the graph, so a replay is still one ``cudaGraphLaunch`` per rank.
+        The caller owns the index contract for ``basis_i32`` (values in [0, num_bases)) on every replay."""
         self._require_cuda()
         if x0_packed.dtype != torch.uint16 or basis_i32.dtype != torch.int32 or not x0_packed.is_cuda or not basis_i32.is_cuda:
             raise ValueError("make_train_graph needs device tensors: x0_packed uint16[B], basis_i32 int32[B]")
+        _lib.check_index(basis_i32, self.model.num_bases, "basis")
+        world, rank = self._dp(process_group, data_parallel)
+        if row_offset is None:
+            row_offset = rank * x0_packed.shape[0] if world > 1 else 0
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            self._train_step_tc(x0_packed, basis_i32, optimizer, row_offset)      # warm-up: allocations, kernel attributes
+            for _ in range(2 if world > 1 else 1):     # warm-up: allocations, kernel attributes, NCCL communicator set-up
+                self._train_step_tc(x0_packed, basis_i32, optimizer, row_offset, process_group, world)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         saved = (optimizer.step_count, self._train_steps, self.model.native_version)
         with torch.cuda.graph(graph):
-            loss = self._train_step_tc(x0_packed, basis_i32, optimizer, row_offset)
+            loss = self._train_step_tc(x0_packed, basis_i32, optimizer, row_offset, process_group, world)
         # capturing launched nothing: put the host-side counters back where the device-side state is
         optimizer.step_count, self._train_steps, self.model.native_version = saved
         self.model.mark_shadow_current()

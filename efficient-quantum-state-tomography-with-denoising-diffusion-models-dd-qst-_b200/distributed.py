@@ -37,10 +37,16 @@ def all_reduce_histograms(hist: torch.Tensor, group=None) -> torch.Tensor:
     return hist
 
 
-def sample_sharded(diffusion, bases, n_shots: int, group=None, reduce: bool = True):
-    """Every rank samples its shard of (bases x shots) and contributes to the full uint32[len(bases), 2^N] table."""
-    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank(group) if world > 1 else 0
+def sample_sharded(diffusion, bases, n_shots: int, group=None, reduce: bool = True, rank: int | None = None,
+                   world: int | None = None):
+    """Every rank samples its shard of (bases x shots) and contributes to the full uint32[len(bases), 2^N] table.
+    ``rank`` / ``world`` default to the process group's; passing them explicitly (with ``reduce=False``) produces the
+    contribution of any rank of any job size on this GPU."""
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+    elif rank is None or not 0 <= rank < world:
+        raise ValueError("rank must be given with world, 0 <= rank < world")
     bases = list(bases)
     N = diffusion.model.num_qubits
     hist = torch.zeros(len(bases), 1 << N, dtype=torch.uint32, device=diffusion.device)

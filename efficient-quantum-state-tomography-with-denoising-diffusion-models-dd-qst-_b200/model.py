@@ -195,6 +195,9 @@ class ConditionalD3PM(nn.Module):
         if not x.is_cuda or not self.flat_params.is_cuda:
             raise RuntimeError("ConditionalD3PM.forward has no CPU path: move the model and inputs to a B200 (cuda)")
         lib = _lib.load()
+        if not _lib.capturing():          # nn.Embedding raises IndexError in the reference (RQC/model.py:59-61)
+            _lib.check_index(t, self.num_timesteps + 1, "t")
+            _lib.check_index(basis_idx, self.num_bases, "basis_idx")
         xp = pack_bits(x, self.num_qubits)
         t32 = t.to(torch.int32).contiguous()
         b32 = basis_idx.to(torch.int32).contiguous()

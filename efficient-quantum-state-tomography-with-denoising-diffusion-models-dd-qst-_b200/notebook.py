@@ -90,6 +90,9 @@ class _NotebookMLP(nn.Module):
         """noisy_x[B] int64 in {0,1}, t[B], basis_id[B] -> logits[B,2] (NB c6:86-102)."""
         if not noisy_x.is_cuda or not self.flat_params.is_cuda:
             raise RuntimeError("the notebook MLPs have no CPU path here: move the model and inputs to a B200 (cuda)")
+        if not _lib.capturing():
+            _lib.check_index(t, self.num_timesteps + 1, "t")
+            _lib.check_index(basis_id, self.num_bases, "basis_id")
         xp = noisy_x.reshape(-1).to(torch.int32).to(torch.uint16).contiguous()
         t32 = t.to(torch.int32).contiguous()
         b32 = basis_id.to(torch.int32).contiguous()
@@ -126,6 +129,7 @@ class BitstringDDM:
         if stream_id is None:
             stream_id = self._calls
             self._calls += 1
+        _lib.check_index(t, self.num_timesteps + 1, "t")
         x0p = x_0.to(self.device).reshape(-1).to(torch.int32).to(torch.uint16).contiguous()
         t32 = t.to(self.device).to(torch.int32).contiguous()
         xtp = torch.empty_like(x0p)
@@ -146,6 +150,7 @@ class BitstringDDM:
         """T reverse steps of "sample x0-hat, re-noise to t-1" (NB c6:189-221) -> bits[num_samples]."""
         lib = _lib.load()
         m = self.model
+        _lib.check_index(int(basis_id), m.num_bases, "basis_id")
         out = torch.empty(num_samples, dtype=torch.uint8, device=self.device)
         ws = _lib.workspace.get(lib.ddqst_mlp_workspace_bytes(C.byref(m.dims), min(num_samples, 65536)), self.device)
         _lib.check(lib.ddqst_mlp_sample(C.byref(m.dims), _lib.ptr(m.flat_params), _lib.ptr(self._sched), int(basis_id), num_samples,

@@ -189,6 +189,35 @@ def denoiser_forward(sd: dict, x: torch.Tensor, t: torch.Tensor, basis: torch.Te
     return out.view(-1, num_qubits, 2)
 
 
+def default_init_state_dict(num_qubits, num_bases, num_timesteps, embed_dim, hidden_dim, num_blocks, variant="B", seed=0):
+    """A reference-shaped ``state_dict`` with torch's default initialisation, built from plain ``torch.nn`` modules in
+    the reference's construction order (RQC/model.py:27-49; variant A: SS/model.py:47-66) under ``torch.manual_seed(seed)``
+    -- so it equals what the reference's own constructor produces under that seed, without importing any product code."""
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    E, H, N = embed_dim, hidden_dim, num_qubits
+    mods = {}
+    if variant == "B":
+        mods["x_emb"] = nn.Embedding(2, E)
+        mods["input_proj"] = nn.Linear(N * E, H)
+        mods["time_emb"] = nn.Embedding(num_timesteps + 1, E)
+        mods["basis_emb"] = nn.Embedding(num_bases, E)
+    else:
+        mods["time_emb"] = nn.Embedding(num_timesteps + 1, E)
+        mods["basis_emb"] = nn.Embedding(num_bases, E)
+        mods["input_proj"] = nn.Linear(N, H)
+    for i in range(num_blocks):
+        mods[f"blocks.{i}.film.net"] = nn.Linear(2 * E, 2 * H)
+        mods[f"blocks.{i}.net.0"] = nn.Linear(H, H)
+        mods[f"blocks.{i}.net.2"] = nn.Linear(H, H)
+    mods["output_head"] = nn.Linear(H, 2 * N)
+    sd = {}
+    for name, m in mods.items():
+        for k, v in m.state_dict().items():
+            sd[f"{name}.{k}"] = v.detach().clone()
+    return sd
+
+
 def notebook_mlp_forward(sd: dict, x: torch.Tensor, t: torch.Tensor, basis: torch.Tensor) -> torch.Tensor:
     """SimpleMLP NB c6:86-102 / UpgradedMLP NB c12:89-94: cat[x.float(), t_emb, b_emb] -> Linear/ReLU stack -> [B,2]."""
     h = torch.cat([x.float().view(-1, 1), F.embedding(t, sd["time_emb.weight"]), F.embedding(basis, sd["basis_emb.weight"])], dim=1)

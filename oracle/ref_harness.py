@@ -29,6 +29,7 @@ import torch
 from . import ddqst_oracle as orc
 
 REF_ROOT = "/root/reference"
+LOCAL_REF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")      # oracle/make_ref.py: verbatim copies of the path's modules
 PHASES = {
     "SS": "versions/multi_qubit_special_states",
     "AS": "versions/multi_qubit_any_state",
@@ -38,7 +39,19 @@ NOTEBOOK = "versions/single_qubit_phase/denoising-with-diffusion-phase-1.ipynb"
 
 
 def available() -> bool:
+    """The whole read-only checkout (notebook, Datapoints, every phase) is mounted -- build container only."""
     return os.path.isdir(os.path.join(REF_ROOT, "versions"))
+
+
+def path_root() -> str | None:
+    """Where the hot-path modules (model / diffusion / reconstruct of the RQC and SS phases) can be imported from:
+    the mounted checkout, else the verbatim copy ``oracle/make_ref.py`` placed in ``oracle/_ref`` (which travels to the
+    GPU box), else None."""
+    if available():
+        return REF_ROOT
+    if os.path.exists(os.path.join(LOCAL_REF, "MANIFEST.json")):
+        return LOCAL_REF
+    return None
 
 
 # ---------------------------------------------------------------- qiskit stub
@@ -86,7 +99,10 @@ def load_phase(phase: str, names=("model", "diffusion", "reconstruct")) -> dict:
     """Import reference modules of one phase under private names (phases share file names)."""
     install_qiskit_stub()
     out = {}
-    base = os.path.join(REF_ROOT, PHASES[phase])
+    root = path_root()
+    if root is None:
+        raise FileNotFoundError("neither /root/reference nor oracle/_ref (python oracle/make_ref.py) is present")
+    base = os.path.join(root, PHASES[phase])
     for n in names:
         spec = importlib.util.spec_from_file_location(f"_ddqst_ref_{phase}_{n}", os.path.join(base, n + ".py"))
         mod = importlib.util.module_from_spec(spec)

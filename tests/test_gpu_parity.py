@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 import torch
 
+import guard
 from conftest import golden_state_dict, load_golden
 from oracle import ddqst_oracle as orc
 
@@ -100,43 +101,65 @@ def test_q_sample_bit_exact(dq, tag):
 
 
 # ------------------------------------------------------------------------------------------ reverse sampling
-def _guard_mismatch_ok(got, want, logits_fn, tol):
-    """bits may differ only where the oracle's decision margin |u*(p0+p1) - p1| is below tol."""
-    bad = got != want
-    return bad.sum(), bad
+def _schedule(tag, T):
+    return (orc.cosine_schedule(T), "posterior", "cosine") if tag == "B" else (orc.linear_schedule(T), "renoise", "linear")
+
+
+def _oracle_traj(tag, sd, T, shots, basis, N, seed, off):
+    (betas, Q), mode, _ = _schedule(tag, T)
+    if tag == "B":
+        return orc.p_sample_posterior(sd, betas, Q, shots, basis, N, seed, shot_offset=off, trajectory=True)
+    return orc.p_sample_renoise(sd, Q, shots, basis, N, seed, shot_offset=off, trajectory=True)
 
 
 @pytest.mark.parametrize("tag", ["A", "B"])
 def test_p_sample_fp32_matches_reference_samples(dq, tag):
+    """End-to-end fp32 trajectories against the samples the UNMODIFIED reference produced under the injected stream.
+    Every shot must be identical, except shots whose FIRST divergence from the oracle trajectory is a guard-band draw
+    (tests/guard.py) -- each mismatching shot is replayed step by step to prove that."""
     z = load_golden(f"model_{tag}_small.npz")
     m, (N, NB, T, *_r) = make_model(dq, z, tag)
+    sd = golden_state_dict(z)
     shots, basis, seed, off = (int(v) for v in z["sample_args"])
-    diff = dq.DiscreteDiffusion(m, T, "cuda", schedule="cosine" if tag == "B" else "linear", seed=seed, precision="fp32")
+    (betas, Q), mode, sched = _schedule(tag, T)
+    diff = dq.DiscreteDiffusion(m, T, "cuda", schedule=sched, seed=seed, precision="fp32")
     got = diff.p_sample(shots, basis, N, shot_offset=off)
     assert got.shape == (shots, N) and got.dtype == torch.int64 and got.is_cuda
-    want = z["samples"]
-    # end-to-end trajectories: fp32 logits differ from the CPU reference by ~1e-6, so a draw can flip only when u
-    # lands inside that margin; over 256*3*20 draws (x2 for renoise) that is rare.  Require >= 99% identical shots.
-    same = (got.cpu().numpy() == want).all(axis=1).mean()
-    assert same >= 0.99, same
+    got = got.cpu()
+    want = torch.from_numpy(z["samples"])
+    final, traj = _oracle_traj(tag, sd, T, shots, basis, N, seed, off)
+    assert torch.equal(final, want)                                   # the oracle reproduces the reference fixture bit for bit
+    differing = torch.nonzero((got != want).any(dim=1)).flatten().tolist()
+    assert len(differing) <= max(2, shots // 50), differing           # band draws are rare in fp32
+    for i in differing:
+        x = traj[0][i:i + 1]
+        explained = False
+        for k, t in enumerate(range(T, 0, -1)):
+            x_next, logits = diff.sample_step(x.cuda(), basis, t, shot_offset=off + i)
+            if not explained and not torch.equal(x_next.cpu(), traj[k + 1][i:i + 1]):
+                # first divergence: same x_t on both sides, so the draw must sit inside the guard band
+                want_logits = orc.denoiser_forward(sd, x, torch.full((1,), t), torch.full((1,), basis), N)
+                guard.assert_draws_in_guard_band(x_next, logits, want_logits, mode, x, t, betas, Q, seed, basis, off + i, N,
+                                                 what=f"fp32 e2e shot {i}")
+                explained = True
+            x = x_next.cpu()
+        assert explained
+        assert torch.equal(x[0], got[i])         # the stepwise path and the one-launch path are the same trajectory
 
 
 @pytest.mark.parametrize("tag,prec", [("B", "fp32"), ("A", "fp32"), ("B", "bf16"), ("A", "bf16")])
 def test_teacher_forced_steps(dq, tag, prec):
-    """Feed the oracle's x_t at every step; x_{t-1} must equal the oracle's draw except inside the guard band."""
+    """Feed the oracle's x_t at every step; x_{t-1} must equal the oracle's draw for every (shot, qubit) outside the guard
+    band of that element's measured logit error -- zero exceptions -- and the band itself must stay thin."""
     z = load_golden(f"model_{tag}_small.npz")
     m, (N, NB, T, *_r) = make_model(dq, z, tag)
     sd = golden_state_dict(z)
     seed, basis, shots, off = 4242, 7, 384, 11
-    if tag == "B":
-        betas, Q = orc.cosine_schedule(T)
-        final, traj = orc.p_sample_posterior(sd, betas, Q, shots, basis, N, seed, shot_offset=off, trajectory=True)
-    else:
-        betas, Q = orc.linear_schedule(T)
-        final, traj = orc.p_sample_renoise(sd, Q, shots, basis, N, seed, shot_offset=off, trajectory=True)
-    diff = dq.DiscreteDiffusion(m, T, "cuda", schedule="cosine" if tag == "B" else "linear", seed=seed, precision=prec)
+    (betas, Q), mode, sched = _schedule(tag, T)
+    final, traj = _oracle_traj(tag, sd, T, shots, basis, N, seed, off)
+    diff = dq.DiscreteDiffusion(m, T, "cuda", schedule=sched, seed=seed, precision=prec)
     tol_logit = 1e-4 if prec == "fp32" else 1e-2
-    total = mismatched = 0
+    total = mismatched = band = 0
     for k, t in enumerate(range(T, 0, -1)):
         x_t = traj[k]
         x_prev, logits = diff.sample_step(x_t.cuda(), basis, t, shot_offset=off)
@@ -144,12 +167,11 @@ def test_teacher_forced_steps(dq, tag, prec):
         err = (logits.cpu() - want_logits).abs().max().item()
         scale = want_logits.abs().max().item()
         assert err <= tol_logit * max(1.0, scale) if prec == "fp32" else err <= tol_logit * scale + 1e-3, (t, err, scale)
-        bad = (x_prev.cpu() != traj[k + 1])
-        total += bad.numel()
-        mismatched += int(bad.sum())
-    # fp32: decisions can flip only within ~1e-6 of the threshold; bf16: within the 1e-2 logit tolerance
+        mm, bb, nn = guard.assert_draws_in_guard_band(x_prev, logits, want_logits, mode, x_t, t, betas, Q, seed, basis, off, N,
+                                                      what=f"{tag}/{prec}")
+        mismatched, band, total = mismatched + mm, band + bb, total + nn
     limit = 2e-4 if prec == "fp32" else 2e-2
-    assert mismatched / total <= limit, (mismatched, total)
+    assert band / total <= limit, (mismatched, band, total)
 
 
 def test_sample_histogram_consistency_and_split_invariance(dq):
@@ -424,9 +446,9 @@ def test_pair_kernel_teacher_forced_and_consistency(dq, H, L, N):
         want = orc.denoiser_forward(sd, traj[k], torch.full((shots,), t), torch.full((shots,), basis), N)
         err = (logits.cpu() - want).abs().max().item()
         assert err <= 1e-2 * want.abs().max().item() + 1e-3, (t, err, want.abs().max().item())
-        mism = x_prev.cpu() != traj[k + 1]
-        total += mism.numel()
-        bad += int(mism.sum())
+        mm, bb, nn = guard.assert_draws_in_guard_band(x_prev, logits, want, "posterior", traj[k], t, betas, Q, seed, basis, off, N,
+                                                      what=f"pair H={H}")
+        total, bad = total + nn, bad + bb
     assert bad / total <= 2e-2, (bad, total)
     assert dq._lib.load().ddqst_debug_tc_status() == 0
     bases = [0, basis, 1]
@@ -446,3 +468,187 @@ def test_pair_kernel_teacher_forced_and_consistency(dq, H, L, N):
     he = exact.sample([basis], n_big)[0].view(torch.int32).cpu().numpy().astype(np.float64) / n_big
     tv = 0.5 * np.abs(hb - he).sum()
     assert tv < 0.5 * np.sqrt((1 << N) / n_big) + 0.02, tv
+
+
+# ------------------------------------------------------------------------------------------ the benchmarked configuration
+C4 = dict(N=8, NB=6561, T=100, E=128, H=512, L=4)
+
+
+def _c4_teacher_forced(dq, model, sd, seed, cases, shots, off, logit_rel=1e-2, band_limit=2e-2):
+    """Single reverse steps of the production kernel (sampler_pair_kernel<512>) at the C4 architecture against
+    RQC/diffusion.py:58-79 restated in the oracle: logits within ``logit_rel`` of the largest logit, every draw inside the
+    guard band of its own logit error."""
+    N, T = C4["N"], C4["T"]
+    betas, Q = orc.cosine_schedule(T)
+    diff = dq.DiscreteDiffusion(model, T, "cuda", seed=seed, precision="bf16")
+    g = torch.Generator().manual_seed(seed)
+    total = band = 0
+    worst = 0.0
+    for basis, t in cases:
+        x_t = torch.randint(0, 2, (shots, N), generator=g)
+        x_prev, logits = diff.sample_step(x_t.cuda(), basis, t, shot_offset=off)
+        want = orc.denoiser_forward(sd, x_t, torch.full((shots,), t), torch.full((shots,), basis), N)
+        err, scale = (logits.cpu() - want).abs().max().item(), want.abs().max().item()
+        worst = max(worst, err / scale)
+        assert err <= logit_rel * scale, (basis, t, err, scale)
+        mm, bb, nn = guard.assert_draws_in_guard_band(x_prev, logits, want, "posterior", x_t, t, betas, Q, seed, basis, off, N,
+                                                      what=f"C4 basis {basis}")
+        total, band = total + nn, band + bb
+    assert dq._lib.load().ddqst_debug_tc_status() == 0
+    assert band / total <= band_limit, (band, total)
+    return worst
+
+
+def test_c4_exact_pair_kernel_default_init(dq):
+    """ConditionalD3PM(8, 6561, 100, 128, 512, 4) exactly as bench.py builds it (torch default init, seed 0): first, middle
+    and LAST row of the 6561-row FiLM table Tb, first / middle / last timestep, 300 shots = 3 tiles (a full CTA pair plus
+    a pair with a padding tile) and 257 shots (partial last tile)."""
+    torch.manual_seed(0)
+    m = dq.ConditionalD3PM(**{k: v for k, v in zip(("num_qubits", "num_bases", "num_timesteps", "embed_dim", "hidden_dim", "num_blocks"),
+                                                     (C4["N"], C4["NB"], C4["T"], C4["E"], C4["H"], C4["L"]))})
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    cases = [(b, t) for b in (0, 3280, 6560) for t in (100, 37, 1)]
+    _c4_teacher_forced(dq, m, sd, seed=1234, cases=cases, shots=300, off=7)
+    _c4_teacher_forced(dq, m, sd, seed=99, cases=[(6560, 100), (0, 1)], shots=257, off=1_000_003)
+    # the one-launch T=100 path (what bench.py times) at this architecture: counts are consistent with the emitted bits,
+    # shot-split invariant across an odd tile count, and identical whether a basis is sampled alone or with others
+    diff = dq.DiscreteDiffusion(m, C4["T"], "cuda", seed=1234, precision="bf16")
+    hist, packed = diff.sample([0, 3280, 6560], 300, return_bits=True)
+    h = hist.view(torch.int32).cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(h[i], np.bincount(packed[i].cpu().numpy(), minlength=256))
+    _, p1 = diff.sample([0, 3280, 6560], 129, return_bits=True)
+    _, p2 = diff.sample([0, 3280, 6560], 171, shot_offset=129, return_bits=True)
+    assert torch.equal(torch.cat([p1, p2], dim=1), packed)
+    _, p3 = diff.sample([6560], 300, return_bits=True)
+    assert torch.equal(p3[0], packed[2])
+    assert dq._lib.load().ddqst_debug_tc_status() == 0
+
+
+def _train_c4(dq, steps=2000, batch=1024, seed=5):
+    """A C4-architecture checkpoint trained by the native tensor-core step on synthetic N=8 random-circuit measurement
+    data (all 6561 bases), so the logits have real dynamic range (default-init logits are ~0.1)."""
+    N, NB, T = C4["N"], C4["NB"], C4["T"]
+    torch.manual_seed(0)
+    m = dq.ConditionalD3PM(N, NB, T, C4["E"], C4["H"], C4["L"]).cuda()
+    hist, _, _psi = dq.generate_synthetic_data(N, "rqc", 2000, rqc_depth=6, seed=seed)
+    ds = dq.QuantumStateDataset.from_counts_table(hist, N, seed=seed)
+    diff = dq.DiscreteDiffusion(m, T, "cuda", seed=seed, precision="bf16")
+    opt = dq.NativeAdam(m, lr=1e-3)
+    first = last = None
+    for s in range(steps):
+        x0, basis = ds.batch(s, batch)
+        loss = diff.train_step(x0, basis, opt, validate=False)
+        if s == 0:
+            first = loss.item()
+    last = loss.item()
+    assert dq._lib.load().ddqst_debug_tc_status() == 0
+    return m, first, last
+
+
+def test_c4_exact_pair_kernel_trained_checkpoint(dq):
+    m, first, last = _train_c4(dq)
+    assert last < first - 0.02, (first, last)                      # it did learn something: logits are no longer ~0
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    x = torch.randint(0, 2, (64, 8), generator=torch.Generator().manual_seed(0))
+    scale = orc.denoiser_forward(sd, x, torch.full((64,), 5), torch.full((64,), 17), 8).abs().max().item()
+    assert scale > 0.5, scale                                      # real dynamic range
+    cases = [(0, 100), (3280, 37), (6560, 1), (17, 5), (4242, 73)]
+    worst = _c4_teacher_forced(dq, m, sd, seed=4321, cases=cases, shots=300, off=11)
+    assert worst <= 1e-2
+
+
+# ------------------------------------------------------------------------------------------ the end-to-end entry points
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_sample_to_host_equals_device_path(dq, prec):
+    """ddqst_sample_host (the call bench.py's e2e number is measured through) returns exactly the bytes and counts of
+    ddqst_sample for the same (seed, bases, shot offset)."""
+    z = load_golden("model_B_small.npz")
+    m, (N, NB, T, *_r) = make_model(dq, z, "B")
+    diff = dq.DiscreteDiffusion(m, T, "cuda", seed=31, precision=prec)
+    bases, shots, off = [5, 0, 26], 777, 123
+    hist, packed = diff.sample(bases, shots, shot_offset=off, return_bits=True)
+    ids = torch.tensor(bases, dtype=torch.int32).pin_memory()
+    out = torch.empty(len(bases) * shots, dtype=torch.uint8).pin_memory()
+    cnt = torch.empty(len(bases), 1 << N, dtype=torch.int32).pin_memory()
+    diff.sample_to_host(ids, shots, out, cnt, shot_offset=off)
+    assert torch.equal(out.view(len(bases), shots), packed.cpu())
+    assert torch.equal(cnt, hist.view(torch.int32).cpu())
+    # counts only / bits only
+    cnt2 = torch.empty_like(cnt)
+    diff.sample_to_host(ids, shots, None, cnt2, shot_offset=off)
+    assert torch.equal(cnt2, cnt)
+    out2 = torch.empty_like(out)
+    diff.sample_to_host(ids, shots, out2, None, shot_offset=off)
+    assert torch.equal(out2, out)
+    with pytest.raises(IndexError):
+        diff.sample_to_host(torch.tensor([NB], dtype=torch.int32), 4, None, cnt2[:1])
+
+
+def test_sample_sharded_plan_covers_single_gpu_table(dq):
+    """distributed.sample_sharded for every rank of a 2-, 3- and 8-rank job, run here one rank after the other on this GPU
+    (rank / world passed explicitly, no reduction): the shards' tables add up to exactly the single-GPU table, both when
+    bases >= ranks (split by basis) and when bases < ranks (split by shots)."""
+    z = load_golden("model_B_small.npz")
+    m, (N, NB, T, *_r) = make_model(dq, z, "B")
+    diff = dq.DiscreteDiffusion(m, T, "cuda", seed=8, precision="bf16")
+    for bases, shots in (([3, 9, 1, 0, 22], 333), ([4, 11], 1001)):
+        single = diff.sample(bases, shots)[0].view(torch.int32)
+        for world in (2, 3, 8):
+            acc = torch.zeros_like(single)
+            for rank in range(world):
+                acc += dq.sample_sharded(diff, bases, shots, reduce=False, rank=rank, world=world).view(torch.int32)
+            assert torch.equal(acc, single), (bases, world)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sample_sharded_two_processes_nccl(dq, tmp_path):
+    """Two real ranks (torchrun, NCCL): the all-reduced table equals the single-GPU table bit for bit."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29617", os.path.join(root, "benchmarks", "multi_gpu_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_index_validation_raises_like_the_reference(dq):
+    """nn.Embedding / Q_bar[t] raise IndexError in the reference; the native tables are never indexed out of range."""
+    m = dq.ConditionalD3PM(3, 27, 10, 16, 64, 1).cuda()
+    diff = dq.DiscreteDiffusion(m, 10, "cuda", precision="bf16")
+    x = torch.zeros(4, 3, dtype=torch.long, device="cuda")
+    ok_t, ok_b = torch.ones(4, dtype=torch.long, device="cuda"), torch.zeros(4, dtype=torch.long, device="cuda")
+    with pytest.raises(IndexError):
+        m(x, ok_t * 11, ok_b)
+    with pytest.raises(IndexError):
+        m(x, ok_t, ok_b + 27)
+    with pytest.raises(IndexError):
+        m(x, ok_t, ok_b - 1)
+    with pytest.raises(IndexError):
+        diff.q_sample(x, ok_t * 11)
+    with pytest.raises(IndexError):
+        diff.sample([0, 27], 8)
+    with pytest.raises(IndexError):
+        diff.p_sample(8, -1, 3)
+    with pytest.raises(IndexError):
+        diff.train_step(x, ok_b + 27, dq.NativeAdam(m))
+    assert diff.sample([26], 8)[0].view(torch.int32).sum().item() == 8
+
+
+def test_zero_shot_basis_gives_nan_like_the_reference(dq):
+    """np.mean over an empty sample array is NaN in RQC/reconstruct.py:44; get_coefficient and the linear-inversion kernel
+    agree on that (a MISSING basis gives 0.0, RQC/reconstruct.py:46)."""
+    N = 2
+    data = {name: np.zeros((0 if name == "XX" else 50, N), dtype=np.int64) for name in orc.basis_strings(N)}
+    assert np.isnan(dq.get_coefficient("XX", data))
+    rho = dq.linear_inversion_raw(data, N).cpu().numpy()
+    assert np.isnan(rho).any()
+    hist = torch.zeros(9, 4, dtype=torch.int32, device="cuda")
+    hist[1:, 0] = 50
+    assert np.isnan(dq.linear_inversion_raw(hist, N).cpu().numpy()).any()
+    del data["XX"]
+    assert dq.get_coefficient("XX", data) == 0.0
+    assert np.isfinite(dq.linear_inversion_raw(data, N).cpu().numpy()).all()

@@ -67,3 +67,60 @@ def test_sharding_plan_covers_everything_once():
             seen[b0:b1, s0:s1] += 1
         assert (seen == 1).all(), (n_bases, shots, world)
     assert [shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+
+
+def test_guard_band_checker_accepts_rounding_and_rejects_real_errors():
+    """tests/guard.py itself: bits drawn from logits that differ from the oracle's by a measured error pass; a wrong bit
+    where the draw is not marginal, a wrong qubit lane or a wrong Philox counter fail."""
+    import guard
+    torch.manual_seed(0)
+    N, T, B, seed, basis, off = 5, 20, 512, 3, 4, 17
+    betas, Q = orc.cosine_schedule(T)
+    lin_b, lin_Q = orc.linear_schedule(T)
+    g = torch.Generator().manual_seed(1)
+    for mode, sched in (("posterior", (betas, Q)), ("renoise", (lin_b, lin_Q))):
+        for t in (T, 7, 1):
+            x_t = torch.randint(0, 2, (B, N), generator=g)
+            want = 2.0 * torch.randn(B, N, 2, generator=g)
+            got_logits = want + 2e-2 * torch.randn(B, N, 2, generator=g)            # a bf16-sized logit error
+            got = guard.oracle_reverse_step(mode, got_logits, x_t, t, sched[0], sched[1], seed, basis, off, N)
+            mm, band, total = guard.assert_draws_in_guard_band(got, got_logits, want, mode, x_t, t, sched[0], sched[1], seed,
+                                                               basis, off, N)
+            assert total == B * N and mm <= band < 0.05 * total
+            # (a) flip the bit whose draw is farthest from marginal -> outside the band
+            nominal = guard.oracle_reverse_step(mode, want, x_t, t, sched[0], sched[1], seed, basis, off, N)
+            lo = guard.oracle_reverse_step(mode, want - torch.tensor([0.5, -0.5]), x_t, t, sched[0], sched[1], seed, basis, off, N)
+            hi = guard.oracle_reverse_step(mode, want + torch.tensor([0.5, -0.5]), x_t, t, sched[0], sched[1], seed, basis, off, N)
+            solid = torch.nonzero((lo == hi) & (lo == nominal))
+            bad = got.clone()
+            r, q = (int(v) for v in solid[0])
+            bad[r, q] ^= 1
+            with pytest.raises(AssertionError, match="OUTSIDE the guard band"):
+                guard.assert_draws_in_guard_band(bad, got_logits, want, mode, x_t, t, sched[0], sched[1], seed, basis, off, N)
+            # (b) qubit lanes swapped, (c) wrong shot offset in the Philox counter
+            with pytest.raises(AssertionError):
+                guard.assert_draws_in_guard_band(got.flip(1), got_logits, want, mode, x_t, t, sched[0], sched[1], seed, basis, off, N)
+            shifted = guard.oracle_reverse_step(mode, got_logits, x_t, t, sched[0], sched[1], seed, basis, off + 1, N)
+            with pytest.raises(AssertionError):
+                guard.assert_draws_in_guard_band(shifted, got_logits, want, mode, x_t, t, sched[0], sched[1], seed, basis, off, N)
+
+
+def test_check_index_contract():
+    from ddqst_b200 import _lib
+    _lib.check_index(torch.tensor([0, 5, 8]), 9, "basis")
+    _lib.check_index([], 9, "basis")
+    _lib.check_index(torch.zeros(0, dtype=torch.long), 9, "basis")
+    for bad in (torch.tensor([0, 9]), [-1, 2], 9, torch.tensor([-3])):
+        with pytest.raises(IndexError):
+            _lib.check_index(bad, 9, "basis")
+    with pytest.raises(IndexError):
+        _lib.check_index(torch.tensor([0]), 101, "t", lo=1)
+
+
+def test_build_stamp_is_content_keyed():
+    """_build: the library's stamp is a hash of csrc/ + include/ddqst.h + flags, so a library built from other sources is
+    detected without relying on file times."""
+    from ddqst_b200 import _build, _lib
+    _lib.load()                                        # builds (incrementally) when nvcc is available, else verifies the stamp
+    assert _build.stamp_matches()
+    assert len(_build.expected_stamp()) == 64
