@@ -16,11 +16,11 @@ from .model import ConditionalD3PM, pack_bits, unpack_bits
 from .notebook import BitstringDDM, SimpleMLP, UpgradedMLP
 from .reconstruct import (DensityMatrix, Statevector, basis_strings, get_coefficient, get_metrics, get_pauli_matrix,
                           histogram_samples, linear_inversion, linear_inversion_raw, make_positive_semidefinite,
-                          state_fidelity)
+                          ReconReport, recon_report, state_fidelity)
 
 __all__ = [
     "ConditionalD3PM", "DiscreteDiffusion", "NativeAdam", "TrainGraph", "cosine_schedule", "linear_schedule", "pack_bits", "unpack_bits",
     "DensityMatrix", "Statevector", "basis_strings", "get_coefficient", "get_metrics", "get_pauli_matrix",
-    "histogram_samples", "linear_inversion", "linear_inversion_raw", "make_positive_semidefinite", "state_fidelity",
+    "histogram_samples", "linear_inversion", "linear_inversion_raw", "make_positive_semidefinite", "state_fidelity", "ReconReport", "recon_report",
     "calculate_z_bias", "evaluate", "evaluate_records", "format_raw_counts_for_inversion", "write_metrics_csv", "born_histograms", "counts_records", "generate_synthetic_data", "get_basis_combinations", "synth_state", "QuantumStateDataset", "load_circuit_records", "state_vector_of", "all_reduce_histograms", "sample_sharded", "shard_range", "build",
 ]

@@ -15,6 +15,7 @@ PRECISION_FP32, PRECISION_BF16 = 0, 1
 MODE_POSTERIOR, MODE_RENOISE = 0, 1
 VARIANT_A, VARIANT_B = 0, 1
 KRON_REVERSED, KRON_UNREVERSED = 0, 1
+TARGET_NONE, TARGET_STATEVECTOR, TARGET_MIXED, TARGET_RANK_ONE = range(4)
 OP_FORWARD, OP_SAMPLE, OP_LINEAR_INVERSION, OP_PSD, OP_FIDELITY_MIXED, OP_TRAIN, OP_METRICS = range(7)
 
 
@@ -51,6 +52,7 @@ SIGNATURES = {
     "ddqst_fidelity_pure": (C.c_int, [_P, _P, _I32, _P, _P]),
     "ddqst_fidelity_mixed": (C.c_int, [_P, _P, _I32, _P, _P, _I64, _P]),
     "ddqst_metrics": (C.c_int, [_P, _I32, _P, _P, _I64, _P]),
+    "ddqst_recon_report": (C.c_int, [_P, _I32, _P, C.c_int, _P, _P, _P, _I64, _P]),
     "ddqst_train_forward_backward": (C.c_int, [_DP, _P, _P, _P, _P, _P, _I64, _F, _P, _P, _P, _I64, _P]),
     "ddqst_forward_saved": (C.c_int, [_DP, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
     "ddqst_backward_saved": (C.c_int, [_DP, _P, _P, _P, _P, _I64, _P, _P, _P, _I64, _P]),

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) coeff_table_kernel(const uint32_t* __rest
   uint32_t bx = 0, bz = 0;                               // label-space masks: X-or-Y letters, Y-or-Z letters
   int rem = b;
   for (int i = N - 1; i >= 0; --i) { int d = rem % 3; rem /= 3; if (d != 2) bx |= 1u << i; if (d != 0) bz |= 1u << i; }
-  const double sh = (double)shots[b];
+  double sh = shots ? (double)shots[b] : 0.0;            // shots == NULL: the row sum, which is WHT element 0 (set below)
   auto emit = [&](uint32_t m, int val) {
     if ((int)m < dim && (m & bz) == bz) {
       uint32_t xl = m & bx, zl = m & bz;
@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(256) coeff_table_kernel(const uint32_t* __rest
       for (int i = 0; i < 32; ++i)
         if (!(i & bit)) { int a = v[i], c = v[i | bit]; v[i] = a + c; v[i | bit] = a - c; }
     }
+    if (!shots) sh = (double)__shfl_sync(0xFFFFFFFFu, v[0], 0);
 #pragma unroll
     for (int i = 0; i < 32; ++i) emit((uint32_t)(lane * 32 + i), v[i]);
   } else {
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(256) coeff_table_kernel(const uint32_t* __rest
         v[j] = upper ? other - v[j] : v[j] + other;
       }
     }
+    if (!shots) sh = (double)__shfl_sync(0xFFFFFFFFu, v[0], 0);
 #pragma unroll
     for (int j = 0; j < E; ++j) emit((uint32_t)(j * 32 + lane), v[j]);
   }
@@ -312,7 +314,7 @@ __global__ void rho_assemble_kernel(const int32_t* __restrict__ W, const int64_t
     }
     if (slot == -2) coeff = 1.0;
     else if (slot < 0 || slot >= n_slots) coeff = 0.0;     // no compatible basis: RQC/reconstruct.py:46 (a zero-shot one gives 0/0 = NaN below)
-    else coeff = (double)W[(int64_t)slot * dim + support] / (double)shots[slot];
+    else coeff = (double)W[(int64_t)slot * dim + support] / (shots ? (double)shots[slot] : (double)W[(int64_t)slot * dim]);
     int ny = __popc(xm & (uint32_t)z) & 3;   // (-i)^ny
     double2 v;
     v.x = ny == 0 ? coeff : (ny == 2 ? -coeff : 0.0);
@@ -627,6 +629,29 @@ __global__ void entropy_kernel(const double* __restrict__ ev, int n, double* __r
   for (int i = threadIdx.x; i < n; i += blockDim.x) { double v = ev[i]; if (v > 0.0) s -= v * log2(v); }
   block_sum3(s, z1, z2, scratch);
   if (threadIdx.x == 0) out[0] = s;
+}
+
+// report[1] = sum ev^2 (purity of V diag(ev) V^H), report[2] = -sum ev log2 ev ; single block
+__global__ void spectrum_summary_kernel(const double* __restrict__ ev, int n, double* __restrict__ report) {
+  __shared__ double scratch[96];
+  double p = 0.0, h = 0.0, z = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { double v = ev[i]; p += v * v; if (v > 0.0) h -= v * log2(v); }
+  block_sum3(p, h, z, scratch);
+  if (threadIdx.x == 0) { report[1] = p; report[2] = h; }
+}
+
+// out += Re Tr(A B) = sum_ij Re(A_ij B_ji)
+__global__ void trace_product_kernel(const double2* __restrict__ A, const double2* __restrict__ B, int dim, double* __restrict__ out) {
+  __shared__ double scratch[96];
+  double s = 0.0, z1 = 0.0, z2 = 0.0;
+  const int64_t total = (int64_t)dim * dim;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(e / dim), c = (int)(e % dim);
+    double2 a = A[e], b = B[(int64_t)c * dim + r];
+    s += a.x * b.x - a.y * b.y;
+  }
+  block_sum3(s, z1, z2, scratch);
+  if (threadIdx.x == 0) atomicAdd(out, s);
 }
 
 __global__ void purity_kernel(const double2* __restrict__ rho, int dim, double* __restrict__ out) {
@@ -1238,7 +1263,7 @@ int ddqst_linear_inversion(const uint32_t* hist, const int64_t* shots, int32_t n
   DDQST_REQUIRE(num_qubits >= 1 && num_qubits <= 12, DDQST_EINVAL_SHAPE, "linear inversion supports 1 <= num_qubits <= 12, got %d", num_qubits);
   DDQST_REQUIRE(n_slots >= 0, DDQST_EINVAL_SHAPE, "n_slots=%d", n_slots);
   DDQST_REQUIRE(kron == DDQST_KRON_REVERSED || kron == DDQST_KRON_UNREVERSED, DDQST_EINVAL_SHAPE, "kron=%d", kron);
-  DDQST_REQUIRE(rho && (n_slots == 0 || (hist && shots)), DDQST_EINVAL_SHAPE, "NULL argument");
+  DDQST_REQUIRE(rho && (n_slots == 0 || hist), DDQST_EINVAL_SHAPE, "NULL argument");
   if (!sel) {
     int64_t full = 1;
     for (int i = 0; i < num_qubits; ++i) full *= 3;
@@ -1342,6 +1367,75 @@ int ddqst_fidelity_mixed(const double* rho_a, const double* rho_b, int32_t dim, 
   DDQST_TRY(jacobi_eigh(Tm, dim, evals, VT, jws, s));
   sqrt_sum_sq_kernel<<<1, 256, 0, s>>>(evals, dim, out);
   DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
+
+int ddqst_recon_report(double* rho, int32_t num_qubits, const double* target, int target_kind, double* evals_out,
+                       double* report, void* workspace, int64_t ws_bytes, void* stream) {
+  // PSD projection (RQC/reconstruct.py:48-54) + get_metrics (:69-76) + state_fidelity (RQC/evaluate.py:77) from ONE full
+  // eigendecomposition: rho_psd = V diag(l') V^H with l' = clip+renormalise(l), so purity = sum l'^2, S = -sum l' log2 l',
+  // sqrt(rho_psd) = V diag(sqrt l') V^H.  Only the 2^(N/2) reduced state and -- for a genuinely mixed target -- the matrix
+  // sqrt(rho) sigma sqrt(rho) need eigensolves of their own.
+  DDQST_TRY(check_arch());
+  DDQST_REQUIRE(num_qubits >= 1 && num_qubits <= 12 && rho && report, DDQST_EINVAL_SHAPE, "bad argument");
+  DDQST_REQUIRE(target_kind >= DDQST_TARGET_NONE && target_kind <= DDQST_TARGET_RANK_ONE, DDQST_EINVAL_SHAPE, "target_kind=%d", target_kind);
+  DDQST_REQUIRE(target_kind == DDQST_TARGET_NONE || target, DDQST_EINVAL_SHAPE, "target is NULL");
+  const int dim = 1 << num_qubits;
+  const int64_t nn = (int64_t)dim * dim;
+  const int64_t need = (target_kind == DDQST_TARGET_MIXED ? 5 : 3) * 16 * nn + 16 * dim + 2048;
+  DDQST_REQUIRE(workspace && ws_bytes >= need, DDQST_EWORKSPACE, "recon_report needs %lld workspace bytes, got %lld", (long long)need, (long long)ws_bytes);
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  double2* VT = (double2*)ws;
+  double2* tmp = (double2*)(ws + 16 * nn);                     // reduced state / second eigenvector set
+  char* jws = ws + 32 * nn;                                    // GT + ctl
+  double* evals = (double*)(jws + 16 * nn + 512);              // [dim]
+  double* evals2 = evals + dim;                                // [dim] scratch spectrum of the secondary eigensolves
+  double2* S = nullptr;
+  DDQST_CUDA_OK(cudaMemsetAsync(report, 0, 5 * sizeof(double), s));
+  dim3 grid((dim + 15) / 16, (dim + 15) / 16), blk(16, 16);
+  int rgrid = (int)((nn + 255) / 256);
+  if (rgrid > num_sms() * 4) rgrid = num_sms() * 4;
+  if (dim >= 2) {
+    DDQST_TRY(jacobi_eigh((const double2*)rho, dim, evals, VT, jws, s));
+    clip_normalise_kernel<<<1, 256, 0, s>>>(evals, dim);
+    DDQST_LAUNCH_OK();
+    rebuild_kernel<<<grid, blk, 0, s>>>(VT, evals, dim, 0, (double2*)rho);
+    DDQST_LAUNCH_OK();
+  }
+  spectrum_summary_kernel<<<1, 256, 0, s>>>(evals, dim, report);
+  DDQST_LAUNCH_OK();
+  if (evals_out) DDQST_CUDA_OK(cudaMemcpyAsync(evals_out, evals, 8 * dim, cudaMemcpyDeviceToDevice, s));
+  // fidelity against the target
+  if (target_kind == DDQST_TARGET_STATEVECTOR) {
+    fidelity_pure_kernel<<<rgrid, 256, 0, s>>>((const double2*)target, (const double2*)rho, dim, report);
+    DDQST_LAUNCH_OK();
+  } else if (target_kind == DDQST_TARGET_RANK_ONE) {
+    trace_product_kernel<<<rgrid, 256, 0, s>>>((const double2*)target, (const double2*)rho, dim, report);   // <psi|rho|psi> = Tr(sigma rho)
+    DDQST_LAUNCH_OK();
+  } else if (target_kind == DDQST_TARGET_MIXED) {
+    S = (double2*)(ws + 48 * nn + 16 * dim + 2048);
+    double2* M = S + nn;
+    rebuild_kernel<<<grid, blk, 0, s>>>(VT, evals, dim, 1, S);                                  // sqrt(rho_psd) from the SAME eigenvectors
+    DDQST_LAUNCH_OK();
+    zgemm_kernel<<<grid, blk, 0, s>>>(S, (const double2*)target, dim, tmp);
+    DDQST_LAUNCH_OK();
+    zgemm_kernel<<<grid, blk, 0, s>>>(tmp, S, dim, M);
+    DDQST_LAUNCH_OK();
+    DDQST_TRY(jacobi_eigh(M, dim, evals2, tmp, jws, s));
+    sqrt_sum_sq_kernel<<<1, 256, 0, s>>>(evals2, dim, report);
+    DDQST_LAUNCH_OK();
+  }
+  // half-cut entanglement entropy (RQC/reconstruct.py:72-75)
+  const int lo = 1 << (num_qubits / 2);
+  if (lo >= 2) {
+    partial_trace_kernel<<<(lo * lo + 127) / 128, 128, 0, s>>>((const double2*)rho, dim, lo, tmp);
+    DDQST_LAUNCH_OK();
+    double2* VT2 = tmp + (int64_t)lo * lo;
+    DDQST_TRY(jacobi_eigh(tmp, lo, evals2, VT2, jws, s));
+    entropy_kernel<<<1, 256, 0, s>>>(evals2, lo, report + 3);
+    DDQST_LAUNCH_OK();
+  }
   return DDQST_OK;
 }
 

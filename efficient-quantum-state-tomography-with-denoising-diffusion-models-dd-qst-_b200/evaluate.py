@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from .dataset import load_circuit_records, state_vector_of
-from .reconstruct import DensityMatrix, get_metrics, linear_inversion, state_fidelity
+from .reconstruct import DensityMatrix, recon_report
 
 CSV_COLUMNS = ["ID", "Depth", "Raw_Fidelity", "D3PM_Fidelity", "Raw_Entropy", "D3PM_Entropy", "Bias"]
 
@@ -67,13 +67,12 @@ def evaluate_records(diffusion, records, num_qubits: int, shots_infer: int, verb
         target_dm = DensityMatrix(np.outer(state_vector_of(state_data), state_vector_of(state_data).conj()))   # :71
         depth = state_data.get("depth", 0)
         raw_input = format_raw_counts_for_inversion(state_data["measurements"], num_qubits, device)
-        rho_raw = linear_inversion(raw_input, num_qubits)                                                       # :76
-        fid_raw = state_fidelity(target_dm, rho_raw)
-        _, s_raw, _ = get_metrics(rho_raw, num_qubits)
+        # :75-78 and :85-88 -- linear_inversion + state_fidelity + get_metrics share one eigendecomposition (recon_report)
+        raw = recon_report(raw_input, num_qubits, target_dm)
+        fid_raw, s_raw = raw.fidelity, raw.entropy
         syn_hist, _ = diffusion.sample(all_bases, shots_infer, shot_offset=i * shots_infer)                    # :80-84
-        rho_d3pm = linear_inversion(syn_hist, num_qubits)
-        fid_d3pm = state_fidelity(target_dm, rho_d3pm)
-        _, s_d3pm, _ = get_metrics(rho_d3pm, num_qubits)
+        d3pm = recon_report(syn_hist, num_qubits, target_dm)
+        fid_d3pm, s_d3pm = d3pm.fidelity, d3pm.entropy
         bias = calculate_z_bias(syn_hist, num_qubits)
         if verbose:
             print(f"State {i} (D={depth}): Raw={fid_raw:.3f} -> D3PM={fid_d3pm:.3f}")

@@ -30,17 +30,21 @@ class DensityMatrix:
     is kept so chained native calls do not round-trip through the host."""
 
     def __init__(self, data):
+        self.pure_vector = None                 # set when built from a state vector: lets fidelity skip the mixed-state formula
         if isinstance(data, DensityMatrix):
+            self.pure_vector = data.pure_vector
             data = data.tensor if data.tensor is not None else data.data
         if torch.is_tensor(data):
             t = data.to(torch.complex128)
             if t.dim() == 1:
+                self.pure_vector = t.contiguous()
                 t = torch.outer(t, t.conj())
             self.tensor = t.contiguous()
             self._host = None
         else:
             a = np.asarray(getattr(data, "data", data), dtype=complex)
             if a.ndim == 1:
+                self.pure_vector = a.copy()
                 a = np.outer(a, a.conj())
             self._host = np.ascontiguousarray(a)
             self.tensor = None
@@ -120,13 +124,13 @@ def _compatible_slot_table(keys, num_qubits: int) -> np.ndarray:
 
 
 def _prepare(synthetic_data, num_qubits: int):
-    """-> (hist uint32[n_slots, 2^N], shots int64[n_slots], sel int32[4^N] or None) on the device."""
+    """-> (hist uint32[n_slots, 2^N], shots (None: the kernel takes each row's sum, which is the shot count of that
+    basis in every input form), sel int32[4^N] or None) on the device."""
     dev = _dev()
     N = num_qubits
     if isinstance(synthetic_data, dict):
         keys = list(synthetic_data.keys())
         hist = torch.zeros(max(len(keys), 1), 1 << N, dtype=torch.uint32, device=dev)
-        shots = torch.zeros(max(len(keys), 1), dtype=torch.int64, device=dev)
         for i, k in enumerate(keys):
             s = synthetic_data[k]
             if getattr(s, "ndim", 2) == 1:                 # already a counts row uint32/int[2^N] (evaluate.format_raw_counts_for_inversion)
@@ -134,20 +138,16 @@ def _prepare(synthetic_data, num_qubits: int):
                 row = row.to(dev)
                 row = row.view(torch.int32) if row.dtype == torch.uint32 else row.to(torch.int32)
                 hist[i] = row.view(torch.uint32)
-                shots[i] = int(row.to(torch.int64).sum().item())
             else:
                 hist[i] = histogram_samples(s, N)
-                shots[i] = int(s.shape[0])
         canonical = keys == basis_strings(N)
         sel = None if canonical else torch.from_numpy(_compatible_slot_table(keys, N)).to(dev)
-        return hist[:len(keys)].contiguous(), shots[:len(keys)].contiguous(), sel
+        return hist[:len(keys)].contiguous(), None, sel
     hist = synthetic_data if torch.is_tensor(synthetic_data) else torch.from_numpy(np.ascontiguousarray(synthetic_data))
     hist = hist.to(dev)
     if hist.dtype != torch.uint32:
         hist = hist.to(torch.int32).view(torch.uint32)
-    hist = hist.contiguous()
-    shots = hist.view(torch.int32).to(torch.int64).sum(dim=1)
-    return hist, shots, None
+    return hist.contiguous(), None, None
 
 
 def linear_inversion_raw(synthetic_data, num_qubits: int, convention: str = "reversed") -> torch.Tensor:
@@ -160,7 +160,7 @@ def linear_inversion_raw(synthetic_data, num_qubits: int, convention: str = "rev
     n_slots = hist.shape[0]
     ws = _lib.workspace.get(max(n_slots * dim * 4, 8 * dim * dim) + 256, dev)
     kron = _lib.KRON_REVERSED if convention == "reversed" else _lib.KRON_UNREVERSED
-    _lib.check(lib.ddqst_linear_inversion(_lib.ptr(hist) if n_slots else None, _lib.ptr(shots) if n_slots else None, n_slots,
+    _lib.check(lib.ddqst_linear_inversion(_lib.ptr(hist) if n_slots else None, _lib.ptr(shots), n_slots,
                                           num_qubits, _lib.ptr(sel), kron, _lib.ptr(rho), _lib.ptr(ws), ws.numel(),
                                           _lib.stream_ptr()))
     return rho
@@ -213,6 +213,15 @@ def state_fidelity(target, rho) -> float:
             return x.to(dev).to(torch.complex128).contiguous()
         return torch.from_numpy(np.ascontiguousarray(np.asarray(getattr(x, "data", x), dtype=complex))).to(dev)
 
+    # a density matrix that is |psi><psi| (built from a vector, or Tr sigma^2 = 1 to rounding) takes the pure-target formula
+    for first, second in ((target, rho), (rho, target)):
+        if isinstance(first, DensityMatrix) or (not isinstance(first, Statevector) and np.ndim(getattr(first, "data", first)) == 2):
+            t, kind = _target_kind(first, dev)
+            if kind == _lib.TARGET_STATEVECTOR:
+                return state_fidelity(Statevector(t.cpu().numpy()), second)
+            if kind == _lib.TARGET_RANK_ONE and not (isinstance(second, Statevector) or np.ndim(getattr(second, "data", second)) == 1):
+                other = as_dev(second)
+                return float(torch.sum(t * other.transpose(0, 1)).real.item())       # Tr(sigma rho)
     a, b = as_dev(target), as_dev(rho)
     out = torch.zeros(1, dtype=torch.float64, device=dev)
     if a.dim() == 1 and b.dim() == 1:
@@ -237,3 +246,59 @@ def get_metrics(rho, num_qubits: int):
     _lib.check(lib.ddqst_metrics(_lib.ptr(t), num_qubits, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     p, s, e = out.cpu().tolist()
     return p, s, e
+
+
+class ReconReport:
+    """What the evaluation loop (RQC/evaluate.py:75-88) needs of one reconstruction: ``rho`` (PSD-projected
+    ``DensityMatrix``), ``evals`` (clipped, renormalised spectrum, device tensor), ``fidelity`` (None without a target),
+    ``purity``, ``entropy`` (von Neumann, bits), ``entanglement_entropy`` (low N/2 qubits, bits)."""
+
+    def __init__(self, rho, evals, fidelity, purity, entropy, entanglement_entropy):
+        self.rho, self.evals, self.fidelity = rho, evals, fidelity
+        self.purity, self.entropy, self.entanglement_entropy = purity, entropy, entanglement_entropy
+
+    def metrics(self):
+        """The tuple ``get_metrics(rho, n)`` returns (RQC/reconstruct.py:69-76)."""
+        return self.purity, self.entropy, self.entanglement_entropy
+
+
+def _target_kind(target, dev):
+    """-> (device tensor or None, DDQST_TARGET_*).  A DensityMatrix that is |psi><psi| to rounding (Tr sigma^2 = 1, as the
+    clean-state targets of RQC/evaluate.py:71) is flagged rank one: its Uhlmann fidelity is Tr(sigma rho) exactly."""
+    if target is None:
+        return None, _lib.TARGET_NONE
+    if isinstance(target, Statevector) or (not isinstance(target, DensityMatrix) and np.ndim(getattr(target, "data", target)) == 1):
+        v = target if torch.is_tensor(target) else torch.from_numpy(np.ascontiguousarray(np.asarray(getattr(target, "data", target), dtype=complex)))
+        return v.to(dev).to(torch.complex128).contiguous(), _lib.TARGET_STATEVECTOR
+    dm = target if isinstance(target, DensityMatrix) else DensityMatrix(target)
+    if dm.pure_vector is not None:
+        v = dm.pure_vector if torch.is_tensor(dm.pure_vector) else torch.from_numpy(np.ascontiguousarray(dm.pure_vector))
+        return v.to(dev).to(torch.complex128).contiguous(), _lib.TARGET_STATEVECTOR
+    t = dm.device_tensor()
+    purity = float(torch.sum(t.real ** 2 + t.imag ** 2).item())          # Tr(sigma^2) of a Hermitian sigma
+    trace = float(torch.diagonal(t).real.sum().item())
+    return t, (_lib.TARGET_RANK_ONE if abs(purity - 1.0) < 1e-10 and abs(trace - 1.0) < 1e-10 else _lib.TARGET_MIXED)
+
+
+def recon_report(data, num_qubits: int, target=None, convention: str = "reversed") -> ReconReport:
+    """``linear_inversion`` + ``state_fidelity(target, rho)`` + ``get_metrics(rho, n)`` (RQC/evaluate.py:75-78) with ONE full
+    eigendecomposition instead of five (ddqst_recon_report).  ``data``: whatever ``linear_inversion`` accepts, or an already
+    assembled raw rho (complex tensor / DensityMatrix [2^N, 2^N])."""
+    lib = _lib.load()
+    dim = 1 << num_qubits
+    if isinstance(data, DensityMatrix):
+        rho = data.device_tensor().clone()
+    elif torch.is_tensor(data) and data.is_complex():
+        rho = data.to(_dev()).to(torch.complex128).contiguous().clone()
+    else:
+        rho = linear_inversion_raw(data, num_qubits, convention)
+    dev = rho.device
+    tgt, kind = _target_kind(target, dev)
+    evals = torch.empty(dim, dtype=torch.float64, device=dev)
+    report = torch.empty(5, dtype=torch.float64, device=dev)
+    nbytes = (5 if kind == _lib.TARGET_MIXED else 3) * 16 * dim * dim + 16 * dim + 2048
+    ws = _lib.workspace.get(nbytes, dev)
+    _lib.check(lib.ddqst_recon_report(_lib.ptr(rho), num_qubits, _lib.ptr(tgt), kind, _lib.ptr(evals), _lib.ptr(report),
+                                      _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    f, p, s, e, _ = report.cpu().tolist()
+    return ReconReport(DensityMatrix(rho), evals, None if kind == _lib.TARGET_NONE else f, p, s, e)

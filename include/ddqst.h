@@ -20,6 +20,13 @@
  *     DDQST_EUNSUPPORTED_ARCH.
  *   - bitstrings: outcome index s = sum_q bit_q << q (column q of the reference's [B,N] tensors =
  *     qubit q = bit q).  "packed" = one uint8 per shot when N <= 8, one uint16 when 9 <= N <= 16.
+ *   - index contract: timestep arrays (t in [0, num_timesteps]; [1, num_timesteps] for sampling) and basis index
+ *     arrays (in [0, num_bases)) that live in DEVICE memory are used to index the embedding / FiLM / schedule
+ *     tables unchecked -- validating them would cost a device synchronisation per call.  The caller owns that
+ *     contract; the Python mirror enforces it (IndexError, as nn.Embedding / Q_bar[t] raise in the reference,
+ *     RQC/model.py:59-61, RQC/diffusion.py:48) on every entry that is not inside a CUDA-graph capture.
+ *     Scalar and host-array indices (ddqst_sample_step, ddqst_sample_host, ddqst_mlp_sample) are checked here
+ *     and fail with DDQST_EINVAL_SHAPE.
  *   - randomness: Philox4x32-10, counter (shot_lo32, stream, t | site<<16, (q>>2) | shot_hi24<<8),
  *     key = seed; word for qubit q = lane q&3; u = (word>>8) * 2^-24; draw bit = u*(p0+p1) < p1.
  *     `stream` is the basis index when sampling and the step / call counter when noising.
@@ -56,6 +63,11 @@ enum { DDQST_MODE_POSTERIOR = 0 /* RQC/diffusion.py:53-80 */, DDQST_MODE_RENOISE
 /* arithmetic of the denoiser GEMMs */
 enum { DDQST_PRECISION_FP32 = 0 /* CUDA-core fp32, the "exact" mode used for end-to-end parity */,
        DDQST_PRECISION_BF16 = 1 /* tcgen05 bf16 x bf16 -> fp32 accumulators in TMEM (production) */ };
+
+/* what `target` points to in ddqst_recon_report */
+enum { DDQST_TARGET_NONE = 0, DDQST_TARGET_STATEVECTOR = 1 /* complex128[2^N] */, DDQST_TARGET_MIXED = 2 /* complex128[2^N,2^N] */,
+       DDQST_TARGET_RANK_ONE = 3 /* complex128[2^N,2^N] known to be |psi><psi| (RQC/evaluate.py:71 wraps the clean state
+                                    vector in a DensityMatrix): F = Tr(sigma rho), no second eigensolve */ };
 
 /* Kronecker convention of get_pauli_matrix */
 enum { DDQST_KRON_REVERSED = 0 /* RQC/reconstruct.py:19 label[::-1] */, DDQST_KRON_UNREVERSED = 1 /* SS/reconstruct.py:13-15 */ };
@@ -126,7 +138,8 @@ int ddqst_pack_bits(const int64_t* bits, int64_t batch, int32_t num_qubits, uint
 int ddqst_unpack_bits(const void* packed, int elem_bytes, int64_t batch, int32_t num_qubits, int64_t* bits, void* stream);
 
 /* ---- R1+R2+R3: linear_inversion before the PSD step (RQC/reconstruct.py:26-46,5-24,56-66).
- * hist[n_slots, 2^N] uint32, shots[n_slots] (row sums; 0 -> coefficient 0), sel[4^N] int32 = histogram
+ * hist[n_slots, 2^N] uint32, shots[n_slots] (row sums; NULL = derived from hist in the kernel; a zero-shot basis
+ * gives 0/0 = NaN as np.mean([]) does in the reference), sel[4^N] int32 = histogram
  * slot feeding each Pauli string in product order (-1: none compatible -> 0.0, -2: identity -> 1.0;
  * NULL = complete product-order data: slot = P with I->X).  rho: complex128[2^N,2^N] row-major,
  * OVERWRITTEN.  workspace: n_slots * 2^N int32 (Walsh-Hadamard coefficients). */
@@ -148,6 +161,17 @@ int ddqst_fidelity_mixed(const double* rho_a, const double* rho_b, int32_t dim, 
 /* ---- get_metrics (RQC/reconstruct.py:69-76): out[3] = purity, von Neumann entropy (bits),
  * entanglement entropy of the low num_qubits/2 qubits. */
 int ddqst_metrics(const double* rho, int32_t num_qubits, double* out, void* workspace, int64_t ws_bytes, void* stream);
+
+/* ---- R4 + get_metrics + F1 from ONE full eigendecomposition (the evaluation loop RQC/evaluate.py:75-88 calls
+ * linear_inversion, state_fidelity and get_metrics back to back on the same rho):
+ *   rho[2^N,2^N] complex128: raw Hermitian in, PSD-projected (RQC/reconstruct.py:48-54) out;
+ *   target / target_kind: see DDQST_TARGET_*;  evals_out (nullable) [2^N]: clipped, renormalised spectrum;
+ *   report[5] = { fidelity (0 when no target), purity Tr rho^2, von Neumann entropy (bits),
+ *                 entanglement entropy of the low N/2 qubits (bits), reserved }.
+ * Eigensolves: one of size 2^N, one of size 2^(N/2), plus one of size 2^N only for DDQST_TARGET_MIXED.
+ * workspace: 3 (5 for DDQST_TARGET_MIXED) * 16 * 4^N + 16 * 2^N + 2048 bytes. */
+int ddqst_recon_report(double* rho, int32_t num_qubits, const double* target, int target_kind, double* evals_out,
+                       double* report, void* workspace, int64_t ws_bytes, void* stream);
 
 /* ---- T1: training step (RQC/main.py:105-115): forward with saved activations, mean cross-entropy,
  * backward into the flat gradient buffer (OVERWRITTEN), loss -> loss_out[0].  x_t/t as produced by

@@ -652,3 +652,44 @@ def test_zero_shot_basis_gives_nan_like_the_reference(dq):
     del data["XX"]
     assert dq.get_coefficient("XX", data) == 0.0
     assert np.isfinite(dq.linear_inversion_raw(data, N).cpu().numpy()).all()
+
+
+# ------------------------------------------------------------------------------------------ one-eigensolve evaluation report
+def test_recon_report_matches_separate_calls_and_reference_fixtures(dq):
+    """ddqst_recon_report (PSD + metrics + fidelity from one eigendecomposition) against the reference-generated fixtures
+    (rho, get_metrics) of the shipped N=3 records, 1e-5."""
+    z = load_golden("datapoints_N3.npz")
+    for i in range(int(z["n"][0])):
+        hist = torch.from_numpy(z[f"r{i}.hist"].astype(np.int32)).cuda()
+        psi = z[f"r{i}.psi"]
+        rep = dq.recon_report(hist, 3, dq.DensityMatrix(np.outer(psi, psi.conj())))       # RQC/evaluate.py:71 form (2-D target)
+        assert np.abs(rep.rho.data - z[f"r{i}.rho"]).max() < 1e-5
+        assert np.allclose(rep.metrics(), z[f"r{i}.metrics"], atol=1e-5)
+        assert abs(rep.fidelity - orc.state_fidelity(psi, z[f"r{i}.rho"])) < 1e-5
+        rep2 = dq.recon_report(hist, 3, dq.Statevector(psi))
+        assert abs(rep2.fidelity - rep.fidelity) < 1e-9
+        assert dq.recon_report(hist, 3).fidelity is None
+        ev = np.sort(rep.evals.cpu().numpy())
+        assert np.allclose(ev, np.sort(np.linalg.eigvalsh(z[f"r{i}.rho"])), atol=1e-9) and abs(ev.sum() - 1) < 1e-12
+
+
+@pytest.mark.parametrize("N", [2, 4, 6, 8])
+def test_recon_report_mixed_target_against_oracle(dq, N):
+    rng = np.random.default_rng(40 + N)
+    dim = 1 << N
+    psi = orc.haar_state(N, seed=N)
+    names = orc.basis_strings(N)
+    hist = np.stack([rng.multinomial(3000, orc.born_probabilities(psi, N, b)) for b in names]).astype(np.int64)
+    want_rho = orc.linear_inversion_hist(hist, N)
+    sigma = 0.8 * np.outer(psi, psi.conj()) + 0.2 * np.eye(dim) / dim                     # a genuinely mixed target (C5 form)
+    h = torch.from_numpy(hist.astype(np.int32)).cuda()
+    rep = dq.recon_report(h, N, dq.DensityMatrix(sigma))
+    assert np.abs(rep.rho.data - want_rho).max() < 1e-5
+    assert np.allclose(rep.metrics(), orc.get_metrics(want_rho, N), atol=1e-5)
+    assert abs(rep.fidelity - orc.state_fidelity(sigma, want_rho)) < 1e-5
+    # the separate entry points agree with the fused report
+    rho = dq.linear_inversion(h, N)
+    assert abs(dq.state_fidelity(dq.DensityMatrix(sigma), rho) - rep.fidelity) < 1e-7
+    assert np.allclose(dq.get_metrics(rho, N), rep.metrics(), atol=1e-7)
+    pure = dq.recon_report(h, N, psi)
+    assert abs(pure.fidelity - orc.state_fidelity(psi, want_rho)) < 1e-5
