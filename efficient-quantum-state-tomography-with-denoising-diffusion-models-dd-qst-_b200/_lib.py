@@ -78,6 +78,7 @@ SIGNATURES = {
     "ddqst_selftest_gemm_tc_dbg": (C.c_int, [_P, _P, C.c_int, C.c_int, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "ddqst_debug_tc_trace": (C.c_int, [_P, _I32]),
     "ddqst_debug_tc_status": (C.c_int, []),
+    "ddqst_debug_ft_stamps": (C.c_int, [_P]),
 }
 
 _lib = None

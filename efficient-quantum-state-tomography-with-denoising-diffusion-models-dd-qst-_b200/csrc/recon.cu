@@ -381,10 +381,11 @@ struct JacobiCtl {            // lives in the 512 bytes between G and the eigenv
   int rotations[64];
   int sweeps_done;
   unsigned int max_ratio2[48];     // ring kernel: per sweep, float bits of max |gamma|^2 / (a b) seen BEFORE rotating
+  float stop_ratio2;               // a sweep that starts with every |gamma|^2 / (a b) below this is the last one
 };
 static_assert(sizeof(JacobiCtl) <= 512, "JacobiCtl must fit the gap in the eigensolver workspace");
 
-__global__ void jacobi_init_kernel(const double2* __restrict__ A, int n, double2* __restrict__ GT, JacobiCtl* ctl) {
+__global__ void jacobi_init_kernel(const double2* __restrict__ A, int n, double2* __restrict__ GT, JacobiCtl* ctl, float stop_ratio2) {
   // single block: Frobenius norm -> sigma, then GT = columns of A + sigma I.  The eigenvector matrix is never
   // accumulated: at convergence G = A'V has orthogonal columns lambda'_j v_j with lambda'_j >= sigma/2 > 0, so
   // v_j = g_j / ||g_j|| (jacobi_evals_kernel) -- half the rotation work and memory traffic of tracking V.
@@ -397,6 +398,7 @@ __global__ void jacobi_init_kernel(const double2* __restrict__ A, int n, double2
   if (threadIdx.x == 0) {
     ctl->sigma = sigma;
     ctl->sweeps_done = 0;
+    ctl->stop_ratio2 = stop_ratio2;
     for (int i = 0; i < 64; ++i) ctl->rotations[i] = 0;
     for (int i = 0; i < 48; ++i) ctl->max_ratio2[i] = 0u;
   }
@@ -611,6 +613,34 @@ __global__ void zgemm_kernel(const double2* __restrict__ A, const double2* __res
     __syncthreads();
   }
   if (r < n && c < n) C[(int64_t)r * n + c] = make_double2(ax, ay);
+}
+
+// Rayleigh-quotient refinement: evals[j] = Re(v_j^H M v_j) for the rows v_j of VT.  jacobi_eigh works on M + sigma I
+// (sigma = 2 ||M||_F), so its eigenvalues carry an ABSOLUTE error of a few hundred ulp of sigma (~4e-14 for ||M|| ~ 1):
+// harmless for rho itself, but the fidelity sums SQUARE ROOTS of the spectrum, and a rank-deficient rho_psd (clipped
+// eigenvalues) gives M = sqrt(rho) sigma sqrt(rho) a large null space -- ~n/2 eigenvalues of +-4e-14 contribute
+// sqrt(4e-14) = 2e-7 each, 2e-5 in total.  The Rayleigh quotient of the (accurate) eigenvectors has no cancellation:
+// its error is second order in the eigenvector error plus plain rounding (~1e-16), which restores 1e-7 in the fidelity.
+__global__ void __launch_bounds__(256) rayleigh_kernel(const double2* __restrict__ M, const double2* __restrict__ VT, int n,
+                                                       double* __restrict__ evals) {
+  extern __shared__ double2 vj[];
+  __shared__ double scratch[96];
+  const int j = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) vj[i] = VT[(int64_t)j * n + i];
+  __syncthreads();
+  double acc = 0.0, z1 = 0.0, z2 = 0.0;
+  for (int a = warp; a < n; a += 8) {
+    double yr = 0.0, yi = 0.0;
+    for (int b = lane; b < n; b += 32) {
+      double2 m = M[(int64_t)a * n + b], v = vj[b];
+      yr += m.x * v.x - m.y * v.y;
+      yi += m.x * v.y + m.y * v.x;
+    }
+    // Re(conj(v_a) * y_a), summed over the lanes' partial y
+    acc += vj[a].x * yr + vj[a].y * yi;
+  }
+  block_sum3(acc, z1, z2, scratch);
+  if (threadIdx.x == 0) evals[j] = acc;
 }
 
 // out[0] = (sum_j sqrt(max(ev_j,0)))^2 ; single block
@@ -864,7 +894,7 @@ __global__ void __launch_bounds__(kJcThreads) jacobi_ring_kernel(double2* __rest
     if (total == 0) { ++sweep; break; }
     // Quadratic convergence: a sweep that started with every |gamma| / sqrt(a b) below 1e-7 leaves them at ~1e-14 --
     // already at the rounding level of the columns -- so the all-quiet verification sweep that would follow is skipped.
-    if (sweep < 48 && __uint_as_float(__ldcg(&ctl->max_ratio2[sweep])) < 1e-14f) { ++sweep; break; }
+    if (sweep < 48 && __uint_as_float(__ldcg(&ctl->max_ratio2[sweep])) < __ldcg(&ctl->stop_ratio2)) { ++sweep; break; }
   }
   if (active) {                                       // after whole sweeps every column is back in its home slot
 #pragma unroll
@@ -1032,7 +1062,7 @@ __global__ void __launch_bounds__(kJcThreads) jacobi_oddeven_kernel(double2* __r
     jc_cluster_barrier();
     const int total = __ldcg(&ctl->rotations[sweep]);
     if (total == 0) { ++sweep; break; }
-    if (sweep < 48 && __uint_as_float(__ldcg(&ctl->max_ratio2[sweep])) < 1e-14f) { ++sweep; break; }
+    if (sweep < 48 && __uint_as_float(__ldcg(&ctl->max_ratio2[sweep])) < __ldcg(&ctl->stop_ratio2)) { ++sweep; break; }
   }
   if (active) {                                       // after whole sweeps warp k holds positions 2k, 2k+1 again
 #pragma unroll
@@ -1143,10 +1173,13 @@ static int launch_jacobi_cluster(double2* GT, int n, int max_sweeps, double tol,
 
 // Hermitian eigendecomposition of A[n,n] (n a power of two >= 2): evals[n], VT (rows = eigenvectors).
 // ws: GT[n*n] double2, then JacobiCtl.
-static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char* ws, cudaStream_t s) {
+// stop_ratio2: see JacobiCtl.  The eigenvalue problem is solved on A + sigma I (sigma = 2 ||A||_F), so a relative off-diagonal
+// |gamma| / sqrt(a b) = r between two columns whose eigenvalues differ by `gap` means an eigenvector mixing of r sigma / (2 gap):
+// 1e-7 is ample for rho itself; the mixed-state fidelity (square roots of a rank-deficient spectrum) asks for 1e-12.
+static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char* ws, cudaStream_t s, float stop_ratio2 = 1e-14f) {
   double2* GT = (double2*)ws;
   JacobiCtl* ctl = (JacobiCtl*)(ws + (int64_t)16 * n * n);
-  jacobi_init_kernel<<<1, 1024, 0, s>>>(A, n, GT, ctl);
+  jacobi_init_kernel<<<1, 1024, 0, s>>>(A, n, GT, ctl, stop_ratio2);
   DDQST_LAUNCH_OK();
   int max_sweeps = 60;
   double tol = 1e-15;
@@ -1197,6 +1230,14 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
     DDQST_CUDA_OK(cudaLaunchCooperativeKernel((void*)jacobi_sweeps_kernel, dim3(grid), dim3(256), args, 0, s));
   }
   jacobi_evals_kernel<<<n, 128, 0, s>>>(GT, n, ctl, evals, VT);
+  DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
+
+static int launch_rayleigh(const double2* M, const double2* VT, int n, double* evals, cudaStream_t s) {
+  const size_t smem = (size_t)n * 16;
+  if (smem > 48 * 1024) DDQST_CUDA_OK(cudaFuncSetAttribute(rayleigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rayleigh_kernel<<<n, 256, smem, s>>>(M, VT, n, evals);
   DDQST_LAUNCH_OK();
   return DDQST_OK;
 }
@@ -1364,7 +1405,8 @@ int ddqst_fidelity_mixed(const double* rho_a, const double* rho_b, int32_t dim, 
   zgemm_kernel<<<grid, blk, 0, s>>>(Tm, S, dim, VT);                            // M = sqrt(a) b sqrt(a) (reuse VT storage)
   DDQST_LAUNCH_OK();
   DDQST_CUDA_OK(cudaMemcpyAsync(Tm, VT, 16 * nn, cudaMemcpyDeviceToDevice, s));
-  DDQST_TRY(jacobi_eigh(Tm, dim, evals, VT, jws, s));
+  DDQST_TRY(jacobi_eigh(Tm, dim, evals, VT, jws, s, 1e-24f));
+  DDQST_TRY(launch_rayleigh(Tm, VT, dim, evals, s));
   sqrt_sum_sq_kernel<<<1, 256, 0, s>>>(evals, dim, out);
   DDQST_LAUNCH_OK();
   return DDQST_OK;
@@ -1422,7 +1464,8 @@ int ddqst_recon_report(double* rho, int32_t num_qubits, const double* target, in
     DDQST_LAUNCH_OK();
     zgemm_kernel<<<grid, blk, 0, s>>>(tmp, S, dim, M);
     DDQST_LAUNCH_OK();
-    DDQST_TRY(jacobi_eigh(M, dim, evals2, tmp, jws, s));
+    DDQST_TRY(jacobi_eigh(M, dim, evals2, tmp, jws, s, 1e-24f));
+    DDQST_TRY(launch_rayleigh(M, tmp, dim, evals2, s));
     sqrt_sum_sq_kernel<<<1, 256, 0, s>>>(evals2, dim, report);
     DDQST_LAUNCH_OK();
   }

@@ -26,6 +26,14 @@
 namespace ddqst {
 
 constexpr int kGtThreads = 192;
+// thread geometry of the fused forward + data-gradient kernel (train_fused.cuh) and of its tile-private array layout
+constexpr int kFtEpiWarps = 16;            // 4 per TMEM lane quarter: warp w owns rows 32*(w%4).., columns (w/4)*32.. of every 128-column chunk
+constexpr int kFtEpiThreads = kFtEpiWarps * 32;
+constexpr int kFtColsPerWarp = 128 / (kFtEpiWarps / 4);
+constexpr int kFtBatches = kFtColsPerWarp / 16;
+constexpr int kFtThreads = kFtEpiThreads + 64;   // + warp 8 (TMA) + warp 9 (MMA, TMEM alloc).  10 warps = at most 3 per SM sub-partition,
+                                                 // so ptxas may use 168 registers per thread (a 16 + 2-warp layout is capped at 96 and spilled
+                                                 // ~500 B per thread into local memory, which misses L1 here: shared memory takes the carve-out)
 template <int BN> __host__ __device__ constexpr int gt_stages() { return BN <= 64 ? 8 : 6; }
 constexpr int kGtMaxZ = 32;
 
@@ -244,14 +252,32 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* mapA_p, const CUten
       const int c = n0 + c0;                      // first global column of this chunk
       if (EPI == TE_STORE) {
         if (rv && c < G.N) {
-          float* o = G.o0 + G.out_zoff[z] + (int64_t)r * G.ld + c;
+          const int64_t oe = G.out_zoff[z] + (int64_t)r * G.ld + c;
           const float* bz = G.bias ? G.bias + (int64_t)z * G.bias_zstride + c : nullptr;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             if (c + i < G.N) {      // N is a multiple of 4
               float4 t = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
               if (bz) { t.x += bz[i]; t.y += bz[i + 1]; t.z += bz[i + 2]; t.w += bz[i + 3]; }
-              *reinterpret_cast<float4*>(o + i) = t;
+              if (G.flag == 2) { v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w; }                       // tile-private bf16, below
+              else if (G.b0) *reinterpret_cast<uint2*>(G.b0 + oe + i) = make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));   // bf16 output
+              else *reinterpret_cast<float4*>(G.o0 + oe + i) = t;
+            }
+          }
+          if (G.flag == 2) {
+            // FiLM vectors for the fused kernel (train_fused.cuh): N = 2H columns (gamma | beta), written in the tile-private layout
+            // [which][tile][chunk][column group][batch][lane quarter][half][lane][8] -- G.ldg = elements of one such array
+            const int Hh = G.N >> 1, nch = Hh >> 7;
+            const int which = c / Hh, cc = c - which * Hh, n = cc >> 7, cw = cc & 127, grp = cw / kFtColsPerWarp, b0 = (cw % kFtColsPerWarp) >> 4;
+            const int64_t tile = r >> 7;
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {
+              const int64_t off = G.out_zoff[z] + (int64_t)which * G.ldg +
+                                  (((((tile * nch + n) * (kFtEpiWarps / 4) + grp) * kFtBatches + b0 + bb) * 4 + warp) * 512) + lane * 8;
+              uint4* p = reinterpret_cast<uint4*>(G.b0 + off);
+              const float* w = v + 16 * bb;
+              p[0] = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
+              p[32] = make_uint4(pack_bf16(w[8], w[9]), pack_bf16(w[10], w[11]), pack_bf16(w[12], w[13]), pack_bf16(w[14], w[15]));
             }
           }
         }
@@ -626,6 +652,7 @@ static int launch_gemm_bn(const HostOperand& A, const HostOperand& B, TcGemm g, 
 struct GroupBuilder {
   TcGroup grp{};
   int total = 0;
+  int bn = 64;                     // N tile of every problem in the group: 128 for large batches (set before the first add())
   int add(const HostOperand& A, const HostOperand& B, TcGemm g, int zcount, int epi = TE_STORE) {
     const int i = grp.n;
     grp.epi[i] = epi;
@@ -633,38 +660,40 @@ struct GroupBuilder {
     if (A.mn_major) DDQST_TRY(make_map3(&grp.mapA[i], A.base, A.mn, A.k, A.batch, A.ld, A.batch_stride, 64));
     else DDQST_TRY(make_map3(&grp.mapA[i], A.base, A.k, A.mn, A.batch, A.ld, A.batch_stride, 128));
     if (B.mn_major) DDQST_TRY(make_map3(&grp.mapB[i], B.base, B.mn, B.k, B.batch, B.ld, B.batch_stride, 64));
-    else DDQST_TRY(make_map3(&grp.mapB[i], B.base, B.k, B.mn, B.batch, B.ld, B.batch_stride, 64));
+    else DDQST_TRY(make_map3(&grp.mapB[i], B.base, B.k, B.mn, B.batch, B.ld, B.batch_stride, bn));
     g.a = TcOperand{A.mn_major, A.kmod, A.zmul};
     g.b = TcOperand{B.mn_major, B.kmod, B.zmul};
     if (g_trace_buf && g_trace_idx < g_trace_cap) g.trace = g_trace_buf + 4 * (g_trace_idx++);
     grp.g[i] = g;
     grp.tiles_m[i] = (g.M + 127) / 128;
-    grp.tiles_n[i] = (g.N + 63) / 64;
+    grp.tiles_n[i] = (g.N + bn - 1) / bn;
     grp.start[i] = total;
     total += grp.tiles_m[i] * grp.tiles_n[i] * zcount;
     grp.start[i + 1] = total;
     grp.n = i + 1;
     return DDQST_OK;
   }
-  int launch(cudaStream_t s) {
+  template <int BN>
+  int launch_bn(cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-      DDQST_CUDA_OK(cudaFuncSetAttribute(gemm_tc_group_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes<64>()));
+      DDQST_CUDA_OK(cudaFuncSetAttribute(gemm_tc_group_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes<BN>()));
       attr_set = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)total);
     cfg.blockDim = dim3(kGtThreads);
-    cfg.dynamicSmemBytes = gt_smem_bytes<64>();
+    cfg.dynamicSmemBytes = gt_smem_bytes<BN>();
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = tc_pdl_enabled() ? 1 : 0;
-    DDQST_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_group_kernel<64>, grp));
+    DDQST_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_group_kernel<BN>, grp));
     return DDQST_OK;
   }
+  int launch(cudaStream_t s) { return bn == 128 ? launch_bn<128>(s) : launch_bn<64>(s); }
 };
 
 // BN = 128 when the grid still covers the machine (or N is not a multiple of 64-wide tiles anyway), else 64
@@ -682,7 +711,7 @@ static int launch_gemm(const HostOperand& A, const HostOperand& B, const TcGemm&
 // ---- workspace
 struct TcWs {
   // bf16 (element offsets into the bf16 region), fp32 (element offsets into the fp32 region)
-  int64_t xin, cond, ind, act, hL, dz, dgb, dh0, dlog, bf_total;
+  int64_t xin, cond, ind, act, hL, dz, dgb, dh0, dlog, z1s, ss, h0s, dsp, gbh, dt, bf_total;
   int64_t gb, h, z1, z2, logits, dres, S, loss_part, f_total;
 };
 static void tc_ws_layout(const ddqst_dims* d, int64_t B, TcWs* w) {
@@ -691,10 +720,12 @@ static void tc_ws_layout(const ddqst_dims* d, int64_t B, TcWs* w) {
   auto take = [&](int64_t n) { int64_t o = off; off = align_up(off + n, 128); return o; };
   w->xin = take(B * N * E); w->cond = take(B * 2 * E); w->ind = take(B * 32); w->act = take(2 * L * B * H); w->hL = take(B * H);
   w->dz = take(2 * L * B * H); w->dgb = take(L * B * 2 * H); w->dh0 = take(B * H); w->dlog = take(B * 32);
+  const int64_t priv = (B + 127) / 128 * 128 * H;     // one tile-private array of the fused pass (rows padded to whole tiles)
+  w->z1s = take(L * priv); w->ss = take(L * priv); w->h0s = take(priv); w->dsp = take(priv); w->gbh = take(L * 2 * priv); w->dt = take(H * 64);
   w->bf_total = off;
   off = 0;
   w->gb = take(L * B * 2 * H); w->h = take((L + 1) * B * H); w->z1 = take(L * B * H); w->z2 = take(L * B * H);
-  w->logits = take(B * 2 * N); w->dres = take(B * H); w->S = take(32 * H); w->loss_part = take((B + 127) / 128 + 8);
+  w->logits = take(B * 2 * N); w->dres = take(B * H); w->S = take(32 * H); w->loss_part = take(4 * ((B + 127) / 128) + 8);
   w->f_total = off;
 }
 
@@ -713,6 +744,98 @@ static int train_tc_supported(const ddqst_dims* d, const ParamLayout& pr) {
   bool ok = (d->variant == DDQST_VARIANT_A || pr.in_w % 8 == 0) && pr.head_w % 8 == 0;
   for (int l = 0; l < d->num_blocks; ++l) ok = ok && pr.film_w[l] % 8 == 0 && pr.w1[l] % 8 == 0 && pr.w2[l] % 8 == 0;
   DDQST_REQUIRE(ok, DDQST_EUNSUPPORTED, "parameter offsets are not 16-byte aligned in the bf16 shadow");
+  return DDQST_OK;
+}
+
+#include "train_fused.cuh"
+
+// collapsed input table as an MMA operand (hi/lo split, K = 32), rebuilt from the CURRENT parameters every step:
+// h0 = c0 + sum_q x_q D[q] with (variant B) c0 = b + sum_q W_q . emb(0), D[q] = W_q . (emb(1) - emb(0)); (variant A) D[q] = W[:, q].
+// Dt[h][k]: k < N hi(D[k][h]); k == N hi(c0[h]); 16 <= k < 16+N lo(D[k-16][h]); k == 16+N lo(c0[h]); else 0.
+__global__ void ft_build_dt_kernel(int variant, int N, int E, int H, const float* __restrict__ x_emb, const float* __restrict__ in_w,
+                                   const float* __restrict__ in_b, __nv_bfloat16* __restrict__ dt) {
+  // one warp per hidden unit h: lanes stride over the embedding index (coalesced reads of W[h, q*E .. q*E+E))
+  const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (h >= H) return;
+  float c = in_b[h];
+  float D[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) D[q] = 0.f;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    if (q < N) {
+      if (variant == DDQST_VARIANT_B) {
+        float d0 = 0.f, d1 = 0.f;
+        const float* w = in_w + (int64_t)h * N * E + q * E;
+        for (int e = lane; e < E; e += 32) { const float wv = w[e]; d0 = fmaf(wv, x_emb[e], d0); d1 = fmaf(wv, x_emb[E + e], d1); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xFFFFFFFFu, d0, o); d1 += __shfl_xor_sync(0xFFFFFFFFu, d1, o); }
+        c += d0;
+        D[q] = d1 - d0;
+      } else {
+        D[q] = in_w[(int64_t)h * N + q];
+      }
+    }
+  }
+  __nv_bfloat16* row = dt + (int64_t)h * 64;
+#pragma unroll
+  for (int kk2 = 0; kk2 < 2; ++kk2) {
+    const int k = lane + 32 * kk2;
+    const int kk = k >= 16 ? k - 16 : k;
+    float out = 0.f;
+    if (k < 32 && kk <= N) {
+      float v = c;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) if (kk == q && q < N) v = D[q];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      out = k < 16 ? __bfloat162float(hi) : v - __bfloat162float(hi);
+    }
+    row[k] = __float2bfloat16_rn(out);
+  }
+}
+
+static bool train_fused_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DDQST_TRAIN_FUSED"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+static bool train_fused_supported(const ddqst_dims* d) {
+  const int H = d->hidden_dim;
+  if (!(H == 128 || H == 256 || H == 512)) return false;
+  if (d->num_qubits > 15) return false;
+  const int smem = 1024 + (H / 64) * 16384 + kFtRing * kFtStage + 2 * d->num_blocks * H * 4 + 256;
+  return smem <= 227 * 1024;
+}
+
+template <int H>
+static int launch_train_fused(const ddqst_dims* d, const ParamLayout& pr, const __nv_bfloat16* shadow, const __nv_bfloat16* dt,
+                              int64_t blk_stride, __nv_bfloat16* act, __nv_bfloat16* hL, __nv_bfloat16* dz, __nv_bfloat16* dh0,
+                              FusedParams P, cudaStream_t s) {
+  const int L = d->num_blocks, N = d->num_qubits;
+  CUtensorMap m_dt, m_w1k, m_w2k, m_w1m, m_w2m, m_hk, m_hm, m_act, m_hL, m_dz, m_dh0;
+  const int64_t bs = blk_stride > 0 ? blk_stride : (int64_t)H * H;
+  DDQST_TRY(make_map3(&m_dt, dt, 64, H, 1, 64, (int64_t)H * 64, 64));
+  DDQST_TRY(make_map3(&m_w1k, shadow + pr.w1[0], H, H, L, H, bs, 64));
+  DDQST_TRY(make_map3(&m_w2k, shadow + pr.w2[0], H, H, L, H, bs, 64));
+  DDQST_TRY(make_map3(&m_w1m, shadow + pr.w1[0], H, H, L, H, bs, 128));
+  DDQST_TRY(make_map3(&m_w2m, shadow + pr.w2[0], H, H, L, H, bs, 128));
+  DDQST_TRY(make_map3(&m_hk, shadow + pr.head_w, H, 2 * N, 1, H, (int64_t)2 * N * H, P.head_pad / 2));
+  DDQST_TRY(make_map3(&m_hm, shadow + pr.head_w, H, 2 * N, 1, H, (int64_t)2 * N * H, P.head_pad));
+  // outputs stored by TMA straight from the A-operand buffer: row-major [z][B][H] bf16, boxes of 32 rows x 64 columns, one per warp (rows past B are clipped)
+  DDQST_TRY(make_map3(&m_act, act, H, P.B, 2 * L, H, P.B * H, 32));
+  DDQST_TRY(make_map3(&m_hL, hL, H, P.B, 1, H, P.B * H, 32));
+  DDQST_TRY(make_map3(&m_dz, dz, H, P.B, 2 * L, H, P.B * H, 32));
+  DDQST_TRY(make_map3(&m_dh0, dh0, H, P.B, 1, H, P.B * H, 32));
+  const int smem = ft_smem_bytes<H>(L);
+  auto kern = train_fused_kernel<H>;
+  static bool attr_set = false;
+  if (!attr_set) { DDQST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+  const int64_t pairs = (P.n_tiles + 1) / 2;
+  const int max_pairs = num_sms() / 2;
+  const int grid_pairs = (int)(pairs < max_pairs ? pairs : max_pairs);
+  P.iters = (int)((pairs + grid_pairs - 1) / grid_pairs);
+  kern<<<2 * grid_pairs, kFtThreads, smem, s>>>(m_dt, m_w1k, m_w2k, m_w1m, m_w2m, m_hk, m_hm, m_act, m_hL, m_dz, m_dh0, P);
+  DDQST_LAUNCH_OK();
   return DDQST_OK;
 }
 
@@ -748,6 +871,38 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
                                                xt, t, basis, xin, cond, ind);
   DDQST_LAUNCH_OK();
 
+  const bool fused = train_fused_enabled() && train_fused_supported(d);
+  if (fused) {
+    // ---------------------------------------------------------------- fused forward + data-gradient pass (train_fused.cuh)
+    __nv_bfloat16 *z1s = bf + w.z1s, *ss = bf + w.ss, *h0s = bf + w.h0s, *dsp = bf + w.dsp, *gbh = bf + w.gbh, *dt = bf + w.dt;
+    const int64_t priv = (B + 127) / 128 * 128 * H;
+    {  // gamma|beta of every block, bf16, tile-private layout: gbh[l] = cond . Wfilm_l^T + bfilm_l
+      TcGemm g = base_gemm((int)B, 2 * H, 2 * E);
+      g.b0 = gbh; g.ld = 2 * H; g.ldg = priv; g.flag = 2; g.bias = params + pr.film_b[0]; g.bias_zstride = blk_stride;
+      for (int l = 0; l < L; ++l) g.out_zoff[l] = (int64_t)l * 2 * priv;
+      HostOperand A = op_k(cond, B, 2 * E, 2 * E);
+      HostOperand Bo{shadow + pr.film_w[0], 0, 2 * H, 2 * E, L, 2 * E, blk_stride > 0 ? blk_stride : (int64_t)2 * H * 2 * E, 0, 1};
+      DDQST_TRY(launch_gemm<TE_STORE>(A, Bo, g, L, s));
+    }
+    ft_build_dt_kernel<<<(H * 32 + 127) / 128, 128, 0, s>>>(d->variant, N, E, H, var_b ? params + pr.x_emb : nullptr, params + pr.in_w,
+                                                       params + pr.in_b, dt);
+    DDQST_LAUNCH_OK();
+    FusedParams P{};
+    P.N = N; P.L = L; P.head_pad = (int)align_up(2 * N, 16); P.B = B; P.n_tiles = (B + 127) / 128;
+    P.xt = xt; P.x0 = x0; P.gb = gbh; P.b1 = params + pr.b1[0]; P.b2 = params + pr.b2[0]; P.bias_stride = blk_stride;
+    P.head_b = params + pr.head_b; P.scale = loss_scale / (float)(B * N);
+    P.dgb = dgb; P.dlog = dlog; P.z1s = z1s; P.ss = ss; P.h0s = h0s; P.dsp = dsp; P.priv_elems = priv;
+    P.loss_part = loss_part;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DDQST_FT_DEBUG"); dbg = e ? atoi(e) : 0; } P.dbg = dbg; }
+    switch (H) {
+      case 128: DDQST_TRY(launch_train_fused<128>(d, pr, shadow, dt, blk_stride, act, hL, dz, dh0, P, s)); break;
+      case 256: DDQST_TRY(launch_train_fused<256>(d, pr, shadow, dt, blk_stride, act, hL, dz, dh0, P, s)); break;
+      default: DDQST_TRY(launch_train_fused<512>(d, pr, shadow, dt, blk_stride, act, hL, dz, dh0, P, s)); break;
+    }
+    loss_finish_tc_kernel<<<1, 32, 0, s>>>(loss_part, (int)(4 * P.n_tiles), 1.0f / (float)(B * N), loss_out);
+    DDQST_LAUNCH_OK();
+    DDQST_CUDA_OK(cudaMemsetAsync(grads, 0, sizeof(float) * pr.total, s));
+  } else {
   // ------------------------------------------------------------------ forward
   {  // gb[l] = cond . Wfilm_l^T + bfilm_l, all blocks in one launch
     TcGemm g = base_gemm((int)B, 2 * H, 2 * E);
@@ -811,10 +966,18 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
       DDQST_TRY(launch_gemm<TE_BW1>(op_k(dz + 2 * l * BH, B, H, H), op_mn(shadow + pr.w1[l], H, H, H), g, 1, s));
     }
   }
+  }   // per-layer (non-fused) path
   // ------------------------------------------------------------------ backward: weight gradients (dY^T . X over the batch)
   // six independent problems (five weight gradients + the FiLM data gradient), one grouped launch
   {
     GroupBuilder grp;
+    {
+      // 128 x 128 tiles once the reduction (= batch) is long enough that operand ingest, not the tile count, bounds the launch:
+      // half the A traffic per FLOP (measured: 268 -> us at batch 8192).  Needs every N of the group to be a multiple of 64.
+      static int thr = -1;
+      if (thr < 0) { const char* e = getenv("DDQST_TC_GROUP_BN128_BATCH"); thr = e ? atoi(e) : 4096; }
+      if (B >= thr && E % 32 == 0) grp.bn = 128;
+    }
     {  // dcond = sum_l dgb_l . Wfilm_l, scattered into the time / basis embedding gradients; the sum over blocks is a
        // split-K over z (one block per z): the epilogue accumulates with atomics anyway
       TcGemm g = base_gemm((int)B, 2 * E, 2 * H);
@@ -889,6 +1052,12 @@ extern "C" {
 int ddqst_debug_tc_trace(long long* buf, int32_t cap) {
   g_trace_buf = buf; g_trace_cap = cap; g_trace_idx = 0;
   return DDQST_OK;
+}
+
+// debugging aid (DDQST_FT_DEBUG=1): clock64 stamps of the fused training kernel, see train_fused.cuh
+int ddqst_debug_ft_stamps(long long* out256_host) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return DDQST_ECUDA;
+  return cudaMemcpyFromSymbol(out256_host, g_ft_dbg, sizeof(long long) * 256) == cudaSuccess ? DDQST_OK : DDQST_ECUDA;
 }
 
 int ddqst_cast_bf16(const float* src, uint16_t* dst, int64_t n, void* stream) {
