@@ -34,7 +34,9 @@ def grads(dq, m, x0p, xtp, t32, b32, tc):
 
 def main():
     import ddqst_b200 as dq
-    out = {"fused": os.environ.get("DDQST_TRAIN_FUSED", "1")}
+    mode = int(os.environ.get("DDQST_TRAIN_FUSED", "1"))
+    dq._lib.load().ddqst_debug_train_path(mode)
+    out = {"fused": mode}
     for name, dims, B in (("h128", (4, 81, 50, 32, 128, 2), 300), ("h256_ragged", (4, 81, 50, 32, 256, 2), 6200),
                           ("c4", (8, 6561, 100, 128, 512, 4), 1024), ("c5", (10, 59049, 100, 128, 512, 4), 1000),
                           ("variantA", (3, 27, 100, 64, 512, 4), 256)):

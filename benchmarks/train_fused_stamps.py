@@ -6,6 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("DDQST_FT_DEBUG", "1")
 import ddqst_b200 as dq
+dq._lib.load().ddqst_debug_train_path(1)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 torch.manual_seed(0)
 m = dq.ConditionalD3PM(8, 6561, 100, 128, 512, 4).cuda()

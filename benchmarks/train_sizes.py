@@ -5,7 +5,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import ddqst_b200 as dq
-out = {"fused": os.environ.get("DDQST_TRAIN_FUSED", "auto"), "bn128_batch": os.environ.get("DDQST_TC_GROUP_BN128_BATCH", "default")}
+dq._lib.load().ddqst_debug_train_path(int(os.environ.get("DDQST_TRAIN_FUSED", "1")))
+out = {"fused": os.environ.get("DDQST_TRAIN_FUSED", "1"), "bn128_batch": os.environ.get("DDQST_TC_GROUP_BN128_BATCH", "default")}
 dims = (8, 6561, 100, 128, 512, 4)
 for B in [int(a) for a in sys.argv[1:]] or [1024, 2048, 4096, 8192]:
     torch.manual_seed(0)

@@ -79,6 +79,7 @@ SIGNATURES = {
     "ddqst_debug_tc_trace": (C.c_int, [_P, _I32]),
     "ddqst_debug_tc_status": (C.c_int, []),
     "ddqst_debug_ft_stamps": (C.c_int, [_P]),
+    "ddqst_debug_train_path": (C.c_int, [C.c_int]),
 }
 
 _lib = None

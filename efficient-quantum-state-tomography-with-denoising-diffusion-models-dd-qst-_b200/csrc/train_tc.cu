@@ -794,10 +794,24 @@ __global__ void ft_build_dt_kernel(int variant, int N, int E, int H, const float
   }
 }
 
-static bool train_fused_enabled() {
+// which forward + data-gradient path a step takes: -1 = by batch size (default), 0 = per-layer GEMM launches, 1 = fused kernel.
+// Initialised from DDQST_TRAIN_FUSED; ddqst_debug_train_path() overrides it (tests compare the two paths in one process).
+static int g_train_fused_mode = -2;
+static int train_fused_mode() {
+  if (g_train_fused_mode == -2) { const char* e = getenv("DDQST_TRAIN_FUSED"); g_train_fused_mode = e ? atoi(e) : -1; }
+  return g_train_fused_mode;
+}
+// The fused kernel keeps a 256-row tile on one SM pair, so a batch of B rows occupies B / 128 SMs: below ~3k rows the per-layer
+// path, which spreads every GEMM over 64+ SMs, has the shorter critical path (measured at 1024 / 2048 / 4096 / 8192 rows:
+// per-layer 0.289 / 0.357 / 0.549 / 1.015 ms, fused 0.343 / 0.384 / 0.474 / 0.629 ms; profiles/r2_train_step.json)
+static int train_fused_min_batch() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("DDQST_TRAIN_FUSED"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
+  if (v < 0) { const char* e = getenv("DDQST_TRAIN_FUSED_MIN_BATCH"); v = e ? atoi(e) : 3072; }
+  return v;
+}
+static bool train_fused_enabled(int64_t batch) {
+  const int m = train_fused_mode();
+  return m == 1 || (m == -1 && batch >= train_fused_min_batch());
 }
 static bool train_fused_supported(const ddqst_dims* d) {
   const int H = d->hidden_dim;
@@ -871,7 +885,7 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
                                                xt, t, basis, xin, cond, ind);
   DDQST_LAUNCH_OK();
 
-  const bool fused = train_fused_enabled() && train_fused_supported(d);
+  const bool fused = train_fused_enabled(B) && train_fused_supported(d);
   if (fused) {
     // ---------------------------------------------------------------- fused forward + data-gradient pass (train_fused.cuh)
     __nv_bfloat16 *z1s = bf + w.z1s, *ss = bf + w.ss, *h0s = bf + w.h0s, *dsp = bf + w.dsp, *gbh = bf + w.gbh, *dt = bf + w.dt;
@@ -973,9 +987,9 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
     GroupBuilder grp;
     {
       // 128 x 128 tiles once the reduction (= batch) is long enough that operand ingest, not the tile count, bounds the launch:
-      // half the A traffic per FLOP (measured: 268 -> us at batch 8192).  Needs every N of the group to be a multiple of 64.
+      // half the A traffic per FLOP (measured: step 0.713 -> 0.629 ms at batch 8192, 0.354 -> 0.343 ms at 1024).  Needs every N of the group to be a multiple of 64.
       static int thr = -1;
-      if (thr < 0) { const char* e = getenv("DDQST_TC_GROUP_BN128_BATCH"); thr = e ? atoi(e) : 4096; }
+      if (thr < 0) { const char* e = getenv("DDQST_TC_GROUP_BN128_BATCH"); thr = e ? atoi(e) : 1024; }
       if (B >= thr && E % 32 == 0) grp.bn = 128;
     }
     {  // dcond = sum_l dgb_l . Wfilm_l, scattered into the time / basis embedding gradients; the sum over blocks is a
@@ -1051,6 +1065,13 @@ extern "C" {
 // register (or clear, with NULL) a device buffer of 4*cap int64 for per-GEMM %globaltimer stamps; resets the launch index
 int ddqst_debug_tc_trace(long long* buf, int32_t cap) {
   g_trace_buf = buf; g_trace_cap = cap; g_trace_idx = 0;
+  return DDQST_OK;
+}
+
+// -1: choose by batch size (default), 0: per-layer GEMM launches, 1: fused forward + data-gradient kernel (where supported)
+int ddqst_debug_train_path(int mode) {
+  DDQST_REQUIRE(mode >= -1 && mode <= 1, DDQST_EINVAL_SHAPE, "mode=%d", mode);
+  g_train_fused_mode = mode;
   return DDQST_OK;
 }
 

@@ -295,6 +295,9 @@ int ddqst_selftest_gemm_tc_dbg(const uint16_t* a, const uint16_t* b, int a_mn, i
 int ddqst_debug_tc_trace(long long* buf, int32_t cap);
 /* synchronises the device; returns the first pipeline-timeout code a tcgen05 kernel recorded (0 = none) */
 int ddqst_debug_tc_status(void);
+/* which forward + data-gradient implementation ddqst_train_forward_backward_tc uses: -1 = by batch size (default; the fused
+ * persistent kernel of csrc/train_fused.cuh from 3072 rows, per-layer GEMM launches below), 0 = per-layer, 1 = fused. */
+int ddqst_debug_train_path(int mode);
 /* debugging aid: with DDQST_FT_DEBUG=1 the fused training kernel records clock64 stamps of its first tile (csrc/train_fused.cuh);
  * copies the 256 int64 values to HOST memory (synchronises the device). */
 int ddqst_debug_ft_stamps(long long* out256_host);

@@ -181,3 +181,29 @@ def test_train_graph_replay_matches_eager(dq):
     assert int(og.step_dev[0].item()) == 4 and og.step_count == 4
     rel = (me.flat_params - mg.flat_params).norm().item() / me.flat_params.norm().item()
     assert rel < 1e-3, rel
+
+
+@pytest.mark.parametrize("dims,B", [((8, 6561, 100, 128, 512, 4), 1024), ((4, 81, 50, 32, 256, 2), 6200), ((4, 81, 50, 32, 128, 2), 300),
+                                    ((10, 59049, 100, 128, 512, 4), 700), ((3, 27, 100, 64, 512, 4), 256)])
+def test_fused_forward_backward_kernel(dq, dims, B):
+    """train_fused_kernel<H> (one persistent cta_group::2 launch for forward + data gradients, csrc/train_fused.cuh) forced on,
+    against the fp32 CUDA-core step (itself pinned to the reference at 1e-5) and against the per-layer tensor-core path:
+    C4 and C5 architectures, a ragged batch with an odd tile count (6200 = 48 tiles + 56 rows), H = 128 / 256 / 512, and the
+    SS variant (E = 64).  Same bars as the per-layer path: loss 5e-3, every gradient tensor 3e-2 relative L2."""
+    lib = dq._lib.load()
+    variant = "A" if dims[3] == 64 else "B"
+    torch.manual_seed(0)
+    m = dq.ConditionalD3PM(*dims, variant=variant).cuda()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.02 * torch.randn_like(p))
+    m.native_version += 1
+    try:
+        dq._lib.check(lib.ddqst_debug_train_path(1))
+        worst_fused = _compare(dq, m, B, dims[2], tol_loss=5e-3, tol_grad=3e-2, seed=1)
+        dq._lib.check(lib.ddqst_debug_train_path(0))
+        worst_layer = _compare(dq, m, B, dims[2], tol_loss=5e-3, tol_grad=3e-2, seed=1)
+    finally:
+        dq._lib.check(lib.ddqst_debug_train_path(-1))
+    # the fused pass keeps more intermediates in bf16 (z1, s, gamma|beta) than the per-layer path: its error may be larger, not by much
+    assert max(worst_fused.values()) <= max(2.5 * max(worst_layer.values()), 1.5e-2), (worst_fused, worst_layer)
