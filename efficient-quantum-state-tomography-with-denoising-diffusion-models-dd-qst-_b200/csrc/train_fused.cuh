@@ -38,7 +38,12 @@ struct FusedParams {
   int64_t B, n_tiles;
   const uint16_t* xt;            // noised bits x_t [B]
   const uint16_t* x0;            // clean bits [B] (cross-entropy targets)
-  const __nv_bfloat16* gb;       // [L][2][tile-private] gamma_l, beta_l (bias folded), written by the FiLM GEMM
+  __nv_bfloat16* gb;             // [L][2][tile-private] gamma_l, beta_l (bias folded): written by the FiLM GEMM launch, or -- film_kc > 0 --
+                                 // by this kernel itself (FiLM phase at the start of every tile)
+  int film_kc, E;                // FiLM in-kernel: number of 128-column K chunks of cond = [t_emb | b_emb] (2E / 128), embed dim
+  const int32_t* t; const int32_t* basis;                   // [B] timestep / basis index of every row
+  const __nv_bfloat16 *temb, *bemb;                         // bf16 shadow of time_emb [T+1, E], basis_emb [num_bases, E]
+  const float* film_b; int64_t film_b_stride;               // fp32 film.net bias of block l: film_b + l * film_b_stride, [2H]
   const float* b1; const float* b2; int64_t bias_stride;   // fp32 parameters: b1 + l * bias_stride
   const float* head_b;
   float scale;                   // loss_scale / (B * N)
@@ -110,7 +115,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFtThreads, 1)
 train_fused_kernel(const __grid_constant__ CUtensorMap map_dt, const __grid_constant__ CUtensorMap map_w1k,
                    const __grid_constant__ CUtensorMap map_w2k, const __grid_constant__ CUtensorMap map_w1m,
                    const __grid_constant__ CUtensorMap map_w2m, const __grid_constant__ CUtensorMap map_headk,
-                   const __grid_constant__ CUtensorMap map_headm, const __grid_constant__ CUtensorMap map_act,
+                   const __grid_constant__ CUtensorMap map_headm, const __grid_constant__ CUtensorMap map_wf,
+                   const __grid_constant__ CUtensorMap map_act,
                    const __grid_constant__ CUtensorMap map_hL, const __grid_constant__ CUtensorMap map_dz,
                    const __grid_constant__ CUtensorMap map_dh0, const FusedParams P) {
   constexpr int NCH = H / 128;
@@ -179,6 +185,19 @@ train_fused_kernel(const __grid_constant__ CUtensorMap map_dt, const __grid_cons
         return s;
       };
       for (int it = 0; it < P.iters; ++it) {
+        if (P.film_kc > 0) {                                              // FiLM phase: gamma_l (rows 0..H of Wfilm_l), beta_l (rows H..2H)
+          for (int g = 0; g < 2 * L; ++g)
+            for (int n = 0; n < NCH; ++n)
+              for (int kc = 0; kc < P.film_kc; ++kc) {
+                uint32_t s = acquire(2 * 16384);
+                uint32_t dst = smem_u32(sRing + s * kFtStage);
+                const int row = (g & 1) * H + n * 128 + (int)crank * 64;
+                if (elected) {
+                  tma_load_3d_2sm(dst, &map_wf, bar_full + 8 * s, (2 * kc) * 64, row, g >> 1);
+                  tma_load_3d_2sm(dst + 8192, &map_wf, bar_full + 8 * s, (2 * kc + 1) * 64, row, g >> 1);
+                }
+              }
+        }
         for (int n = 0; n < NCH; ++n) {                                   // input table, K block 0 only
           uint32_t s = acquire(2 * 8192);
           if (elected) tma_load_3d_2sm(smem_u32(sRing + s * kFtStage), &map_dt, bar_full + 8 * s, 0, n * 128 + (int)crank * 64, 0);
@@ -245,6 +264,33 @@ train_fused_kernel(const __grid_constant__ CUtensorMap map_dt, const __grid_cons
         ++slot;
       };
       for (int it = 0; it < P.iters; ++it) {
+        // ---- FiLM phase: 2L GEMMs [256 x H] = cond[256 x 2E] . Wfilm_l[half]^T; chunk n may be overwritten once ready[n] says the
+        //      previous stage's epilogue has read it
+        if (P.film_kc > 0) {
+          for (int g = 0; g < 2 * L; ++g) {
+            for (int n = 0; n < NCH; ++n) {
+              mbar_wait_cluster(bar_ready + 8 * n, slot & 1u, 59);
+              tc_fence_after();
+              for (int kc = 0; kc < P.film_kc; ++kc) {
+                uint32_t s = stage_wait();
+                if (elected) {
+                  const uint64_t ad = desc_adv(a_desc0, (uint32_t)kc * 32768u);
+                  const uint64_t bd = desc_adv(b_desc0, s * kFtStage);
+#pragma unroll
+                  for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                      umma2_bf16(tmem_base + n * 128, desc_adv(ad, h * 16384 + j * 32), desc_adv(bd, h * 8192 + j * 32), idesc,
+                                 (uint32_t)((kc | h | j) != 0));
+                }
+                stage_release(s);
+              }
+              if (elected) umma2_commit_mc(bar_acc + 8 * n, 3);
+              __syncwarp();
+            }
+            ++slot;
+          }
+        }
         // ---- input GEMM (K = 32)
         mbar_wait_cluster(bar_ready, slot & 1u, 52);
         tc_fence_after();
@@ -463,8 +509,44 @@ train_fused_kernel(const __grid_constant__ CUtensorMap map_dt, const __grid_cons
       };
       auto no_pre = [&](int, int, uint32_t (&)[8], uint32_t (&)[8], uint32_t (&)[8]) {};
 
-      // ---- input rows: [bits, 1, 0.. | bits, 1, 0..] (hi / lo halves of the collapsed input table), K columns 0..31
       stores_drained();                                     // the previous tile's last bulk stores have read shared memory
+      if (P.film_kc > 0) {
+        // ---- FiLM phase (RQC/model.py:9-10): cond = [time_emb[t] | basis_emb[basis]] is gathered into the A-operand buffer (K blocks
+        //      0 .. 2E/64), then 2L GEMMs against Wfilm_l produce gamma_l / beta_l, which the sweeps below write -- bias added -- into
+        //      the tile-private arrays the later epilogues read.  Replaces a separate GEMM launch of B x 2E x 2HL (14 waves of
+        //      4-K-block CTAs at batch 8192, 118 us).
+        {
+          const int tt = valid ? P.t[grow] : 0, bb = valid ? P.basis[grow] : 0;
+          const int kbt = P.E >> 6;                                      // K blocks of the time half
+          for (int kb = cs; kb < 2 * kbt; kb += kGroups) {
+            const uint4* src = reinterpret_cast<const uint4*>(kb < kbt ? P.temb + (int64_t)tt * P.E + kb * 64
+                                                                       : P.bemb + (int64_t)bb * P.E + (kb - kbt) * 64);
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+              *reinterpret_cast<uint4*>(sA + a_chunk_off(kb, m, ch)) = valid ? __ldg(src + ch) : make_uint4(0, 0, 0, 0);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) signal_ready(c);
+        for (int g = 0; g < 2 * L; ++g) {
+          const float* fb = P.film_b + (int64_t)(g >> 1) * P.film_b_stride + (g & 1) * H;
+          __nv_bfloat16* dst = P.gb + (int64_t)g * P.priv_elems;
+          sweep(67, g + 1 < 2 * L, nullptr, 0, no_pre,
+                [&](int n, int b, int c0, const uint32_t (&r)[16], const uint32_t (&)[8], const uint32_t (&)[8], const uint32_t (&)[8]) {
+                  uint32_t o[8];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(fb + c0) + i);
+                    o[2 * i] = pack_bf16(__uint_as_float(r[4 * i]) + bv.x, __uint_as_float(r[4 * i + 1]) + bv.y);
+                    o[2 * i + 1] = pack_bf16(__uint_as_float(r[4 * i + 2]) + bv.z, __uint_as_float(r[4 * i + 3]) + bv.w);
+                  }
+                  stp(dst, n, b, o);
+                });
+        }
+        // every warp has seen the last FiLM accumulator chunk complete, i.e. all reads of cond by the tensor core are done:
+        // K block 0 may now take the input rows
+      }
+      // ---- input rows: [bits, 1, 0.. | bits, 1, 0..] (hi / lo halves of the collapsed input table), K columns 0..31
       if (worker) {
         const uint32_t xbits = valid ? P.xt[grow] : 0u;
         uint32_t w[8];

@@ -118,7 +118,9 @@ __device__ __forceinline__ void st32_bf16(__nv_bfloat16* p, const float (&v)[32]
 
 // one 128 x BN output tile (bx, by) of batch entry bz; the whole CTA calls it
 template <int BN, int EPI>
-__device__ __forceinline__ void gemm_tile(const CUtensorMap* mapA_p, const CUtensorMap* mapB_p, const TcGemm& G, int bx, int by, int bz) {
+// ks / nks: split-K -- this CTA reduces K blocks [ks * ceil(KB/nks), ...) only and (nks > 1, TE_STORE) ADDS its tile atomically
+__device__ __forceinline__ void gemm_tile(const CUtensorMap* mapA_p, const CUtensorMap* mapB_p, const TcGemm& G, int bx, int by, int bz,
+                                          int ks = 0, int nks = 1) {
   const CUtensorMap& mapA = *mapA_p;
   const CUtensorMap& mapB = *mapB_p;
   constexpr int STAGE = gt_stage_bytes<BN>();
@@ -131,7 +133,8 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* mapA_p, const CUten
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kGtStages), bar_acc = smem_u32(bars + 2 * kGtStages);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = bx * 128, n0 = by * BN, z = bz;
-  const int KB = (G.K + 63) >> 6;
+  const int KBtot = (G.K + 63) >> 6, kb_per = (KBtot + nks - 1) / nks, kb0 = ks * kb_per;
+  const int KB = KBtot - kb0 < kb_per ? KBtot - kb0 : kb_per;      // the host picks nks so that every split is non-empty
 
   // programmatic dependent launch: let the next kernel of the stream start its prologue now; our own inputs are
   // only touched after griddepcontrol.wait below (= the previous kernel has completed and flushed)
@@ -172,7 +175,7 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* mapA_p, const CUten
         // instruction in an ELECT / BRA.U.ANY loop)
         const uint32_t full = bar_full + 8 * s;
         const uint32_t dstA = smem_u32(smem + s * STAGE), dstB = dstA + 16384;
-        const int kg = kb * 64;
+        const int kg = (kb0 + kb) * 64;
         int ka = kg, za = z * G.a.zmul, kbb = kg, zb = z * G.b.zmul;
         if (G.a.kmod > 0) { za += kg / G.a.kmod; ka = kg % G.a.kmod; }
         if (G.b.kmod > 0) { zb += kg / G.b.kmod; kbb = kg % G.b.kmod; }
@@ -258,8 +261,11 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* mapA_p, const CUten
           for (int i = 0; i < 32; i += 4) {
             if (c + i < G.N) {      // N is a multiple of 4
               float4 t = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-              if (bz) { t.x += bz[i]; t.y += bz[i + 1]; t.z += bz[i + 2]; t.w += bz[i + 3]; }
-              if (G.flag == 2) { v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w; }                       // tile-private bf16, below
+              if (bz && ks == 0) { t.x += bz[i]; t.y += bz[i + 1]; t.z += bz[i + 2]; t.w += bz[i + 3]; }
+              if (nks > 1) {                       // split-K partial: the output was zeroed by the caller
+                float* o = G.o0 + oe + i;
+                atomicAdd(o, t.x); atomicAdd(o + 1, t.y); atomicAdd(o + 2, t.z); atomicAdd(o + 3, t.w);
+              } else if (G.flag == 2) { v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w; }                       // tile-private bf16, below
               else if (G.b0) *reinterpret_cast<uint2*>(G.b0 + oe + i) = make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));   // bf16 output
               else *reinterpret_cast<float4*>(G.o0 + oe + i) = t;
             }
@@ -403,7 +409,7 @@ struct TcGroup {
   CUtensorMap mapA[kGtMaxGroup], mapB[kGtMaxGroup];
   TcGemm g[kGtMaxGroup];
   int start[kGtMaxGroup + 1];
-  int tiles_m[kGtMaxGroup], tiles_n[kGtMaxGroup];
+  int tiles_m[kGtMaxGroup], tiles_n[kGtMaxGroup], zcount[kGtMaxGroup], ksplit[kGtMaxGroup];
   int epi[kGtMaxGroup];            // TE_STORE or TE_DCOND
   int n;
 };
@@ -416,8 +422,9 @@ __global__ void __launch_bounds__(kGtThreads) gemm_tc_group_kernel(const __grid_
     if (k < P.n && lin >= P.start[k]) i = k;
   const int local = lin - P.start[i];
   const int tm = P.tiles_m[i], tn = P.tiles_n[i];
-  if (P.epi[i] == TE_DCOND) gemm_tile<BN, TE_DCOND>(&P.mapA[i], &P.mapB[i], P.g[i], local % tm, (local / tm) % tn, local / (tm * tn));
-  else gemm_tile<BN, TE_STORE>(&P.mapA[i], &P.mapB[i], P.g[i], local % tm, (local / tm) % tn, local / (tm * tn));
+  const int zc = P.zcount[i], z = (local / (tm * tn)) % zc, ks = local / (tm * tn * zc);
+  if (P.epi[i] == TE_DCOND) gemm_tile<BN, TE_DCOND>(&P.mapA[i], &P.mapB[i], P.g[i], local % tm, (local / tm) % tn, z);
+  else gemm_tile<BN, TE_STORE>(&P.mapA[i], &P.mapB[i], P.g[i], local % tm, (local / tm) % tn, z, ks, P.ksplit[i]);
 }
 
 // ------------------------------------------------------------------------------------ small CUDA-core kernels
@@ -653,6 +660,7 @@ struct GroupBuilder {
   TcGroup grp{};
   int total = 0;
   int bn = 64;                     // N tile of every problem in the group: 128 for large batches (set before the first add())
+  bool split_k = false;            // outputs are pre-zeroed gradient buffers: long reductions may be split over CTAs
   int add(const HostOperand& A, const HostOperand& B, TcGemm g, int zcount, int epi = TE_STORE) {
     const int i = grp.n;
     grp.epi[i] = epi;
@@ -667,8 +675,19 @@ struct GroupBuilder {
     grp.g[i] = g;
     grp.tiles_m[i] = (g.M + 127) / 128;
     grp.tiles_n[i] = (g.N + bn - 1) / bn;
+    grp.zcount[i] = zcount;
+    // split-K for the long reductions (weight gradients reduce over the batch): without it a problem is tiles_m x tiles_n CTAs that
+    // each walk the whole batch -- at batch 8192 that is 224 CTAs of 128 K-blocks next to 500 short ones, two badly filled waves.
+    // ~32 K-blocks per CTA; the partial tiles are added atomically into the (pre-zeroed) gradient buffer.
+    int ks = 1;
+    if (epi == TE_STORE && split_k && g.bias == nullptr && g.b0 == nullptr) {
+      const int kbt = (g.K + 63) / 64;
+      ks = (kbt + 31) / 32;
+      while (ks > 1 && ((kbt + ks - 1) / ks) * (ks - 1) >= kbt) --ks;     // every split non-empty
+    }
+    grp.ksplit[i] = ks;
     grp.start[i] = total;
-    total += grp.tiles_m[i] * grp.tiles_n[i] * zcount;
+    total += grp.tiles_m[i] * grp.tiles_n[i] * zcount * ks;
     grp.start[i + 1] = total;
     grp.n = i + 1;
     return DDQST_OK;
@@ -826,7 +845,7 @@ static int launch_train_fused(const ddqst_dims* d, const ParamLayout& pr, const 
                               int64_t blk_stride, __nv_bfloat16* act, __nv_bfloat16* hL, __nv_bfloat16* dz, __nv_bfloat16* dh0,
                               FusedParams P, cudaStream_t s) {
   const int L = d->num_blocks, N = d->num_qubits;
-  CUtensorMap m_dt, m_w1k, m_w2k, m_w1m, m_w2m, m_hk, m_hm, m_act, m_hL, m_dz, m_dh0;
+  CUtensorMap m_dt, m_w1k, m_w2k, m_w1m, m_w2m, m_hk, m_hm, m_wf, m_act, m_hL, m_dz, m_dh0;
   const int64_t bs = blk_stride > 0 ? blk_stride : (int64_t)H * H;
   DDQST_TRY(make_map3(&m_dt, dt, 64, H, 1, 64, (int64_t)H * 64, 64));
   DDQST_TRY(make_map3(&m_w1k, shadow + pr.w1[0], H, H, L, H, bs, 64));
@@ -835,6 +854,11 @@ static int launch_train_fused(const ddqst_dims* d, const ParamLayout& pr, const 
   DDQST_TRY(make_map3(&m_w2m, shadow + pr.w2[0], H, H, L, H, bs, 128));
   DDQST_TRY(make_map3(&m_hk, shadow + pr.head_w, H, 2 * N, 1, H, (int64_t)2 * N * H, P.head_pad / 2));
   DDQST_TRY(make_map3(&m_hm, shadow + pr.head_w, H, 2 * N, 1, H, (int64_t)2 * N * H, P.head_pad));
+  {  // FiLM weights [L][2H rows][2E], K-major boxes of 64 x 64
+    const int E2 = 2 * d->embed_dim;
+    const int64_t fbs = L > 1 ? pr.film_w[1] - pr.film_w[0] : (int64_t)2 * H * E2;
+    DDQST_TRY(make_map3(&m_wf, shadow + pr.film_w[0], E2, 2 * H, L, E2, fbs, 64));
+  }
   // outputs stored by TMA straight from the A-operand buffer: row-major [z][B][H] bf16, boxes of 32 rows x 64 columns, one per warp (rows past B are clipped)
   DDQST_TRY(make_map3(&m_act, act, H, P.B, 2 * L, H, P.B * H, 32));
   DDQST_TRY(make_map3(&m_hL, hL, H, P.B, 1, H, P.B * H, 32));
@@ -848,7 +872,7 @@ static int launch_train_fused(const ddqst_dims* d, const ParamLayout& pr, const 
   const int max_pairs = num_sms() / 2;
   const int grid_pairs = (int)(pairs < max_pairs ? pairs : max_pairs);
   P.iters = (int)((pairs + grid_pairs - 1) / grid_pairs);
-  kern<<<2 * grid_pairs, kFtThreads, smem, s>>>(m_dt, m_w1k, m_w2k, m_w1m, m_w2m, m_hk, m_hm, m_act, m_hL, m_dz, m_dh0, P);
+  kern<<<2 * grid_pairs, kFtThreads, smem, s>>>(m_dt, m_w1k, m_w2k, m_w1m, m_w2m, m_hk, m_hm, m_wf, m_act, m_hL, m_dz, m_dh0, P);
   DDQST_LAUNCH_OK();
   return DDQST_OK;
 }
@@ -890,6 +914,12 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
     // ---------------------------------------------------------------- fused forward + data-gradient pass (train_fused.cuh)
     __nv_bfloat16 *z1s = bf + w.z1s, *ss = bf + w.ss, *h0s = bf + w.h0s, *dsp = bf + w.dsp, *gbh = bf + w.gbh, *dt = bf + w.dt;
     const int64_t priv = (B + 127) / 128 * 128 * H;
+    // FiLM GEMMs inside the fused kernel when cond's K = 2E is a whole number of 128-column chunks and the embedding rows are 16-byte
+    // aligned in the bf16 shadow; otherwise a separate launch writes the same tile-private arrays
+    static int film_env = -1;
+    if (film_env < 0) { const char* e = getenv("DDQST_TRAIN_FILM_IN_KERNEL"); film_env = (e && e[0] == '0') ? 0 : 1; }
+    const bool film_in_kernel = film_env == 1 && (2 * E) % 128 == 0 && 2 * E <= H && pr.time_emb % 8 == 0 && pr.basis_emb % 8 == 0 && E % 8 == 0;
+    if (!film_in_kernel)
     {  // gamma|beta of every block, bf16, tile-private layout: gbh[l] = cond . Wfilm_l^T + bfilm_l
       TcGemm g = base_gemm((int)B, 2 * H, 2 * E);
       g.b0 = gbh; g.ld = 2 * H; g.ldg = priv; g.flag = 2; g.bias = params + pr.film_b[0]; g.bias_zstride = blk_stride;
@@ -905,6 +935,8 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
     P.N = N; P.L = L; P.head_pad = (int)align_up(2 * N, 16); P.B = B; P.n_tiles = (B + 127) / 128;
     P.xt = xt; P.x0 = x0; P.gb = gbh; P.b1 = params + pr.b1[0]; P.b2 = params + pr.b2[0]; P.bias_stride = blk_stride;
     P.head_b = params + pr.head_b; P.scale = loss_scale / (float)(B * N);
+    P.film_kc = film_in_kernel ? (2 * E) / 128 : 0; P.E = E; P.t = t; P.basis = basis;
+    P.temb = shadow + pr.time_emb; P.bemb = shadow + pr.basis_emb; P.film_b = params + pr.film_b[0]; P.film_b_stride = blk_stride;
     P.dgb = dgb; P.dlog = dlog; P.z1s = z1s; P.ss = ss; P.h0s = h0s; P.dsp = dsp; P.priv_elems = priv;
     P.loss_part = loss_part;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DDQST_FT_DEBUG"); dbg = e ? atoi(e) : 0; } P.dbg = dbg; }
@@ -991,6 +1023,12 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
       static int thr = -1;
       if (thr < 0) { const char* e = getenv("DDQST_TC_GROUP_BN128_BATCH"); thr = e ? atoi(e) : 1024; }
       if (B >= thr && E % 32 == 0) grp.bn = 128;
+      static int sk = -1;
+      // measured at batch 8192 (step 0.584 ms without, 0.618 ms with): the atomic epilogues cost more than the better wave
+      // balance returns, so split-K stays an opt-in (DDQST_TC_SPLIT_K=1)
+      if (sk < 0) { const char* e = getenv("DDQST_TC_SPLIT_K"); sk = (e && e[0] == '1') ? 1 : 0; }
+      grp.split_k = sk == 1;
+      if (grp.split_k) DDQST_CUDA_OK(cudaMemsetAsync(S, 0, sizeof(float) * 32 * H, s));     // S = ind^T . dh0 is accumulated too
     }
     {  // dcond = sum_l dgb_l . Wfilm_l, scattered into the time / basis embedding gradients; the sum over blocks is a
        // split-K over z (one block per z): the epilogue accumulates with atomics anyway

@@ -474,28 +474,39 @@ def test_pair_kernel_teacher_forced_and_consistency(dq, H, L, N):
 C4 = dict(N=8, NB=6561, T=100, E=128, H=512, L=4)
 
 
-def _c4_teacher_forced(dq, model, sd, seed, cases, shots, off, logit_rel=1e-2, band_limit=2e-2):
+def _c4_teacher_forced(dq, model, sd, seed, cases, shots, off, logit_rel=1e-2, band_limit=2e-2, norm="max"):
     """Single reverse steps of the production kernel (sampler_pair_kernel<512>) at the C4 architecture against
-    RQC/diffusion.py:58-79 restated in the oracle: logits within ``logit_rel`` of the largest logit, every draw inside the
-    guard band of its own logit error."""
+    RQC/diffusion.py:58-79 restated in the oracle: logits within ``logit_rel`` relative error, every draw inside the guard
+    band of its own logit error.  ``norm``: 'max' = max |error| / max |logit| of the batch; 'l2' = ||error||_2 / ||logits||_2 of
+    the batch AND max |error| <= logit_rel x the largest logit over all cases (a trained model's logits span 0.3 .. 6 over the
+    timesteps: at high t they are small and a max-norm ratio taken per batch measures the noise floor, not the kernel)."""
     N, T = C4["N"], C4["T"]
     betas, Q = orc.cosine_schedule(T)
     diff = dq.DiscreteDiffusion(model, T, "cuda", seed=seed, precision="bf16")
     g = torch.Generator().manual_seed(seed)
     total = band = 0
     worst = 0.0
+    errs, scales = [], []
     for basis, t in cases:
         x_t = torch.randint(0, 2, (shots, N), generator=g)
         x_prev, logits = diff.sample_step(x_t.cuda(), basis, t, shot_offset=off)
         want = orc.denoiser_forward(sd, x_t, torch.full((shots,), t), torch.full((shots,), basis), N)
         err, scale = (logits.cpu() - want).abs().max().item(), want.abs().max().item()
-        worst = max(worst, err / scale)
-        assert err <= logit_rel * scale, (basis, t, err, scale)
+        if norm == "max":
+            worst = max(worst, err / scale)
+            assert err <= logit_rel * scale, (basis, t, err, scale)
+        else:
+            rel2 = ((logits.cpu() - want).norm() / want.norm()).item()
+            worst = max(worst, rel2)
+            assert rel2 <= logit_rel, (basis, t, rel2, err, scale)
+            errs.append(err); scales.append(scale)
         mm, bb, nn = guard.assert_draws_in_guard_band(x_prev, logits, want, "posterior", x_t, t, betas, Q, seed, basis, off, N,
                                                       what=f"C4 basis {basis}")
         total, band = total + nn, band + bb
     assert dq._lib.load().ddqst_debug_tc_status() == 0
     assert band / total <= band_limit, (band, total)
+    if norm == "l2":
+        assert max(errs) <= logit_rel * max(scales), (errs, scales)
     return worst
 
 
@@ -555,7 +566,7 @@ def test_c4_exact_pair_kernel_trained_checkpoint(dq):
     scale = orc.denoiser_forward(sd, x, torch.full((64,), 5), torch.full((64,), 17), 8).abs().max().item()
     assert scale > 0.5, scale                                      # real dynamic range
     cases = [(0, 100), (3280, 37), (6560, 1), (17, 5), (4242, 73)]
-    worst = _c4_teacher_forced(dq, m, sd, seed=4321, cases=cases, shots=300, off=11)
+    worst = _c4_teacher_forced(dq, m, sd, seed=4321, cases=cases, shots=300, off=11, norm="l2")
     assert worst <= 1e-2
 
 
