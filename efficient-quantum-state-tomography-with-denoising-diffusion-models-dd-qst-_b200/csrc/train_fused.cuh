@@ -49,7 +49,7 @@ struct FusedParams {
   float scale;                   // loss_scale / (B * N)
   __nv_bfloat16 *dgb, *dlog;     // row-major [L][B][2H] (dgamma | dbeta) and [B][32]: stored by the threads
   // row-major act / hL / dz / dh0 (TcWs arrays, inputs of the weight-gradient launch) are written by TMA through the maps
-  __nv_bfloat16 *z1s, *ss, *h0s, *dsp;   // tile-private saves: z1_l [L], s_l [L], h_0, residual gradient; priv_elems each
+  __nv_bfloat16 *d1s, *hs, *dsv, *h0s, *dsp;   // tile-private saves: silu'(z1_l) [L], h_{l+1} [L], silu'(s_l) [L], h_0, residual gradient
   int64_t priv_elems;            // elements of one tile-private array = padded tiles * 128 * H
   float* loss_part;              // [n_tiles * 4] per-warp partial sums of the per-row cross-entropy
 };
@@ -459,13 +459,13 @@ train_fused_kernel(const __grid_constant__ CUtensorMap map_dt, const __grid_cons
         // second register set before this batch's TMEM read; with 16 warps (96 registers, 4 warps per scheduler to hide the
         // latency instead) they are issued into the SAME registers right after this batch's math has consumed them.
         constexpr bool kDouble = kFtEpiWarps <= 8;
-        uint32_t la[8], lb[8], lc[8], na[8], nb[8], nc[8];
-        pre(0, 0, la, lb, lc);
+        uint32_t la[8], lb[8], lc[8], ld[8], na[8], nb[8], nc[8], nd[8];
+        pre(0, 0, la, lb, lc, ld);
 #pragma unroll 1
         for (int idx = 0; idx < kFtBatches * NCH; ++idx) {
           const int n = idx / kFtBatches, b = idx % kFtBatches;
           const int c0 = n * 128 + cs * kFtColsPerWarp + b * 16;
-          if (kDouble && idx + 1 < kFtBatches * NCH) pre((idx + 1) / kFtBatches, (idx + 1) % kFtBatches, na, nb, nc);
+          if (kDouble && idx + 1 < kFtBatches * NCH) pre((idx + 1) / kFtBatches, (idx + 1) % kFtBatches, na, nb, nc, nd);
           if (b == 0) {
             wait_acc(n, code);
             if (n == 0 && stamp) g_ft_dbg[2 * (slot % 50)] = clock64();
@@ -473,12 +473,12 @@ train_fused_kernel(const __grid_constant__ CUtensorMap map_dt, const __grid_cons
           uint32_t r[16];
           tmem_ld16(t_lane + c0, r);
           tmem_wait_ld16(r);
-          body(n, b, c0, r, la, lb, lc);
+          body(n, b, c0, r, la, lb, lc, ld);
           if (kDouble) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { la[i] = na[i]; lb[i] = nb[i]; lc[i] = nc[i]; }
+            for (int i = 0; i < 8; ++i) { la[i] = na[i]; lb[i] = nb[i]; lc[i] = nc[i]; ld[i] = nd[i]; }
           } else if (idx + 1 < kFtBatches * NCH) {
-            pre((idx + 1) / kFtBatches, (idx + 1) % kFtBatches, la, lb, lc);
+            pre((idx + 1) / kFtBatches, (idx + 1) % kFtBatches, la, lb, lc, ld);
           }
           if (b == kFtBatches - 1) {
             if (sig) signal_ready(n);
@@ -507,7 +507,7 @@ train_fused_kernel(const __grid_constant__ CUtensorMap map_dt, const __grid_cons
         if (stamp) g_ft_dbg[2 * (slot % 50) + 1] = clock64();
         ++slot;
       };
-      auto no_pre = [&](int, int, uint32_t (&)[8], uint32_t (&)[8], uint32_t (&)[8]) {};
+      auto no_pre = [&](int, int, uint32_t (&)[8], uint32_t (&)[8], uint32_t (&)[8], uint32_t (&)[8]) {};
 
       stores_drained();                                     // the previous tile's last bulk stores have read shared memory
       if (P.film_kc > 0) {
@@ -532,7 +532,7 @@ train_fused_kernel(const __grid_constant__ CUtensorMap map_dt, const __grid_cons
           const float* fb = P.film_b + (int64_t)(g >> 1) * P.film_b_stride + (g & 1) * H;
           __nv_bfloat16* dst = P.gb + (int64_t)g * P.priv_elems;
           sweep(67, g + 1 < 2 * L, nullptr, 0, no_pre,
-                [&](int n, int b, int c0, const uint32_t (&r)[16], const uint32_t (&)[8], const uint32_t (&)[8], const uint32_t (&)[8]) {
+                [&](int n, int b, int c0, const uint32_t (&r)[16], const uint32_t (&)[8], const uint32_t (&)[8], const uint32_t (&)[8], const uint32_t (&)[8]) {
                   uint32_t o[8];
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
@@ -572,8 +572,8 @@ train_fused_kernel(const __grid_constant__ CUtensorMap map_dt, const __grid_cons
         const __nv_bfloat16* gam = P.gb;                    // [L][2][tile-private]
         const __nv_bfloat16* bet = P.gb + P.priv_elems;
         sweep(60, true, &map_act, 0,
-              [&](int n, int b, uint32_t (&la)[8], uint32_t (&lb)[8], uint32_t (&)[8]) { ldp(gam, n, b, la); ldp(bet, n, b, lb); },
-              [&](int n, int b, int c0, const uint32_t (&r)[16], const uint32_t (&la)[8], const uint32_t (&lb)[8], const uint32_t (&)[8]) {
+              [&](int n, int b, uint32_t (&la)[8], uint32_t (&lb)[8], uint32_t (&)[8], uint32_t (&)[8]) { ldp(gam, n, b, la); ldp(bet, n, b, lb); },
+              [&](int n, int b, int c0, const uint32_t (&r)[16], const uint32_t (&la)[8], const uint32_t (&lb)[8], const uint32_t (&)[8], const uint32_t (&)[8]) {
                 uint32_t o[8], hs[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -586,54 +586,56 @@ train_fused_kernel(const __grid_constant__ CUtensorMap map_dt, const __grid_cons
               });
       }
       for (int l = 0; l < L; ++l) {
-        // ---- E1: z1 = acc + b1 (saved); u = silu(z1)
+        // ---- E1: z1 = acc + b1; u = silu(z1); silu'(z1) saved for the backward half (the same tanh gives both)
         {
           const float* hb1 = sB1 + l * H;
-          __nv_bfloat16* z1p = P.z1s + (int64_t)l * P.priv_elems;
+          __nv_bfloat16* d1p = P.d1s + (int64_t)l * P.priv_elems;
           sweep(61, true, &map_act, 2 * l + 1, no_pre,
-                [&](int n, int b, int c0, const uint32_t (&r)[16], const uint32_t (&)[8], const uint32_t (&)[8], const uint32_t (&)[8]) {
-                  uint32_t o[8], zs[8];
+                [&](int n, int b, int c0, const uint32_t (&r)[16], const uint32_t (&)[8], const uint32_t (&)[8], const uint32_t (&)[8], const uint32_t (&)[8]) {
+                  uint32_t o[8], dv[8];
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
                     const float z0 = __uint_as_float(r[2 * i]) + hb1[c0 + 2 * i], z1 = __uint_as_float(r[2 * i + 1]) + hb1[c0 + 2 * i + 1];
-                    zs[i] = pack_bf16(z0, z1);
-                    o[i] = pack_bf16(silu_half(0.5f * z0), silu_half(0.5f * z1));
+                    const float g0 = ft_sigmoid(z0), g1 = ft_sigmoid(z1);
+                    o[i] = pack_bf16(z0 * g0, z1 * g1);
+                    dv[i] = pack_bf16(g0 * fmaf(z0, 1.0f - g0, 1.0f), g1 * fmaf(z1, 1.0f - g1, 1.0f));
                   }
                   store_sA(c0, o);
-                  stp(z1p, n, b, zs);
+                  stp(d1p, n, b, dv);
                 });
         }
-        // ---- E2: s = h_l + acc + b2 (saved); h = silu(s); a_{l+1} = FiLM_{l+1}(h) (or h itself before the head).
-        //      The residual stream h_l is re-read from what the previous epilogue saved (h_0, or s_{l-1} -> silu) rather than
-        //      living in 64 registers per thread across the whole network.
+        // ---- E2: s = h_l + acc + b2; h_{l+1} = silu(s) and silu'(s) saved; a_{l+1} = FiLM_{l+1}(h) (or h itself before the head).
+        //      The residual stream h_l is re-read from what the previous epilogue saved rather than living in 64 registers per
+        //      thread across the whole network.
         {
           const float* hb2 = sB2 + l * H;
           const bool last = (l == L - 1);
           const __nv_bfloat16* gam = P.gb + (int64_t)(last ? 0 : l + 1) * 2 * P.priv_elems;
           const __nv_bfloat16* bet = gam + P.priv_elems;
-          __nv_bfloat16* sp = P.ss + (int64_t)l * P.priv_elems;
-          const __nv_bfloat16* hsrc = l > 0 ? P.ss + (int64_t)(l - 1) * P.priv_elems : P.h0s;
-          const bool inner = l > 0;
+          __nv_bfloat16* hp = P.hs + (int64_t)l * P.priv_elems;
+          __nv_bfloat16* dp = P.dsv + (int64_t)l * P.priv_elems;
+          const __nv_bfloat16* hsrc = l > 0 ? P.hs + (int64_t)(l - 1) * P.priv_elems : P.h0s;
           sweep(62, true, last ? &map_hL : &map_act, last ? 0 : 2 * (l + 1),
-                [&](int n, int b, uint32_t (&la)[8], uint32_t (&lb)[8], uint32_t (&lc)[8]) {
+                [&](int n, int b, uint32_t (&la)[8], uint32_t (&lb)[8], uint32_t (&lc)[8], uint32_t (&)[8]) {
                   if (!last) { ldp(gam, n, b, la); ldp(bet, n, b, lb); }
                   ldp(hsrc, n, b, lc);
                 },
-                [&](int n, int b, int c0, const uint32_t (&r)[16], const uint32_t (&la)[8], const uint32_t (&lb)[8], const uint32_t (&lc)[8]) {
-                  uint32_t o[8], ssv[8];
+                [&](int n, int b, int c0, const uint32_t (&r)[16], const uint32_t (&la)[8], const uint32_t (&lb)[8], const uint32_t (&lc)[8], const uint32_t (&)[8]) {
+                  uint32_t o[8], hv[8], dv[8];
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
-                    float h0v = bf16_lo(lc[i]), h1v = bf16_hi(lc[i]);
-                    if (inner) { h0v = silu_half(0.5f * h0v); h1v = silu_half(0.5f * h1v); }
-                    const float s0 = h0v + __uint_as_float(r[2 * i]) + hb2[c0 + 2 * i];
-                    const float s1 = h1v + __uint_as_float(r[2 * i + 1]) + hb2[c0 + 2 * i + 1];
-                    ssv[i] = pack_bf16(s0, s1);
-                    const float v0 = silu_half(0.5f * s0), v1 = silu_half(0.5f * s1);
-                    o[i] = last ? pack_bf16(v0, v1)
+                    const float s0 = bf16_lo(lc[i]) + __uint_as_float(r[2 * i]) + hb2[c0 + 2 * i];
+                    const float s1 = bf16_hi(lc[i]) + __uint_as_float(r[2 * i + 1]) + hb2[c0 + 2 * i + 1];
+                    const float g0 = ft_sigmoid(s0), g1 = ft_sigmoid(s1);
+                    const float v0 = s0 * g0, v1 = s1 * g1;
+                    hv[i] = pack_bf16(v0, v1);
+                    dv[i] = pack_bf16(g0 * fmaf(s0, 1.0f - g0, 1.0f), g1 * fmaf(s1, 1.0f - g1, 1.0f));
+                    o[i] = last ? hv[i]
                                 : pack_bf16(fmaf(v0, 1.0f + bf16_lo(la[i]), bf16_lo(lb[i])), fmaf(v1, 1.0f + bf16_hi(la[i]), bf16_hi(lb[i])));
                   }
                   store_sA(c0, o);
-                  stp(sp, n, b, ssv);
+                  stp(hp, n, b, hv);
+                  stp(dp, n, b, dv);
                 });
         }
       }
@@ -683,14 +685,14 @@ train_fused_kernel(const __grid_constant__ CUtensorMap map_dt, const __grid_cons
       // ================================================= backward =================================================
       // ---- B_head: ds_{L-1} = dh_L * silu'(s_{L-1})  (= dz2_{L-1}; also kept tile-private as the residual gradient)
       {
-        const __nv_bfloat16* sp = P.ss + (int64_t)(L - 1) * P.priv_elems;
+        const __nv_bfloat16* dp = P.dsv + (int64_t)(L - 1) * P.priv_elems;
         sweep(64, true, &map_dz, 2 * (L - 1) + 1,
-              [&](int n, int b, uint32_t (&la)[8], uint32_t (&)[8], uint32_t (&)[8]) { ldp(sp, n, b, la); },
-              [&](int n, int b, int c0, const uint32_t (&r)[16], const uint32_t (&la)[8], const uint32_t (&)[8], const uint32_t (&)[8]) {
+              [&](int n, int b, uint32_t (&la)[8], uint32_t (&)[8], uint32_t (&)[8], uint32_t (&)[8]) { ldp(dp, n, b, la); },
+              [&](int n, int b, int c0, const uint32_t (&r)[16], const uint32_t (&la)[8], const uint32_t (&)[8], const uint32_t (&)[8], const uint32_t (&)[8]) {
                 uint32_t o[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                  o[i] = pack_bf16(__uint_as_float(r[2 * i]) * ft_dsilu(bf16_lo(la[i])), __uint_as_float(r[2 * i + 1]) * ft_dsilu(bf16_hi(la[i])));
+                  o[i] = pack_bf16(__uint_as_float(r[2 * i]) * bf16_lo(la[i]), __uint_as_float(r[2 * i + 1]) * bf16_hi(la[i]));
                 store_sA(c0, o);
                 stp(P.dsp, n, b, o);
               });
@@ -698,14 +700,14 @@ train_fused_kernel(const __grid_constant__ CUtensorMap map_dt, const __grid_cons
       for (int l = L - 1; l >= 0; --l) {
         // ---- B2: dz1_l = (dz2_l . W2_l) * silu'(z1_l)
         {
-          const __nv_bfloat16* z1p = P.z1s + (int64_t)l * P.priv_elems;
+          const __nv_bfloat16* d1p = P.d1s + (int64_t)l * P.priv_elems;
           sweep(65, true, &map_dz, 2 * l,
-                [&](int n, int b, uint32_t (&la)[8], uint32_t (&)[8], uint32_t (&)[8]) { ldp(z1p, n, b, la); },
-                [&](int, int, int c0, const uint32_t (&r)[16], const uint32_t (&la)[8], const uint32_t (&)[8], const uint32_t (&)[8]) {
+                [&](int n, int b, uint32_t (&la)[8], uint32_t (&)[8], uint32_t (&)[8], uint32_t (&)[8]) { ldp(d1p, n, b, la); },
+                [&](int, int, int c0, const uint32_t (&r)[16], const uint32_t (&la)[8], const uint32_t (&)[8], const uint32_t (&)[8], const uint32_t (&)[8]) {
                   uint32_t o[8];
 #pragma unroll
                   for (int i = 0; i < 8; ++i)
-                    o[i] = pack_bf16(__uint_as_float(r[2 * i]) * ft_dsilu(bf16_lo(la[i])), __uint_as_float(r[2 * i + 1]) * ft_dsilu(bf16_hi(la[i])));
+                    o[i] = pack_bf16(__uint_as_float(r[2 * i]) * bf16_lo(la[i]), __uint_as_float(r[2 * i + 1]) * bf16_hi(la[i]));
                   store_sA(c0, o);
                 });
         }
@@ -713,26 +715,25 @@ train_fused_kernel(const __grid_constant__ CUtensorMap map_dt, const __grid_cons
         //          l > 0: ds_{l-1} = dh_l * silu'(s_{l-1}) = dz2_{l-1} ; l == 0: dh_0
         {
           const __nv_bfloat16* gam = P.gb + (int64_t)l * 2 * P.priv_elems;                                   // gamma_l
-          const __nv_bfloat16* hsrc = l > 0 ? P.ss + (int64_t)(l - 1) * P.priv_elems : P.h0s;               // s_{l-1} or h_0
+          const __nv_bfloat16* hsrc = l > 0 ? P.hs + (int64_t)(l - 1) * P.priv_elems : P.h0s;               // h_l
+          const __nv_bfloat16* dsrc = P.dsv + (int64_t)(l > 0 ? l - 1 : 0) * P.priv_elems;                   // silu'(s_{l-1})
           __nv_bfloat16* dgp = P.dgb + (int64_t)l * P.B * 2 * H + rowG;
           const bool inner = l > 0;
           sweep(66, inner, inner ? &map_dz : &map_dh0, inner ? 2 * (l - 1) + 1 : 0,
-                [&](int n, int b, uint32_t (&la)[8], uint32_t (&lb)[8], uint32_t (&lc)[8]) { ldp(gam, n, b, la); ldp(hsrc, n, b, lb); ldp(P.dsp, n, b, lc); },
-                [&](int n, int b, int c0, const uint32_t (&r)[16], const uint32_t (&la)[8], const uint32_t (&lb)[8], const uint32_t (&lc)[8]) {
+                [&](int n, int b, uint32_t (&la)[8], uint32_t (&lb)[8], uint32_t (&lc)[8], uint32_t (&ld)[8]) {
+                  ldp(gam, n, b, la); ldp(hsrc, n, b, lb); ldp(P.dsp, n, b, lc);
+                  if (inner) ldp(dsrc, n, b, ld);
+                },
+                [&](int n, int b, int c0, const uint32_t (&r)[16], const uint32_t (&la)[8], const uint32_t (&lb)[8], const uint32_t (&lc)[8], const uint32_t (&ld)[8]) {
                   uint32_t o[8], dg[8], db[8];
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
                     const float da0 = __uint_as_float(r[2 * i]), da1 = __uint_as_float(r[2 * i + 1]);
-                    const float p0 = bf16_lo(lb[i]), p1 = bf16_hi(lb[i]);              // s_{l-1} (inner) or h_0
-                    float h0v = p0, h1v = p1, d0 = 1.f, d1 = 1.f;
-                    if (inner) {
-                      const float sg0 = ft_sigmoid(p0), sg1 = ft_sigmoid(p1);
-                      h0v = p0 * sg0; h1v = p1 * sg1;                                  // h_l = silu(s_{l-1})
-                      d0 = sg0 * fmaf(p0, 1.0f - sg0, 1.0f); d1 = sg1 * fmaf(p1, 1.0f - sg1, 1.0f);
-                    }
-                    dg[i] = pack_bf16(da0 * h0v, da1 * h1v);
+                    dg[i] = pack_bf16(da0 * bf16_lo(lb[i]), da1 * bf16_hi(lb[i]));
                     db[i] = pack_bf16(da0, da1);
-                    o[i] = pack_bf16(fmaf(da0, 1.0f + bf16_lo(la[i]), bf16_lo(lc[i])) * d0, fmaf(da1, 1.0f + bf16_hi(la[i]), bf16_hi(lc[i])) * d1);
+                    float dh0v = fmaf(da0, 1.0f + bf16_lo(la[i]), bf16_lo(lc[i])), dh1v = fmaf(da1, 1.0f + bf16_hi(la[i]), bf16_hi(lc[i]));
+                    if (inner) { dh0v *= bf16_lo(ld[i]); dh1v *= bf16_hi(ld[i]); }
+                    o[i] = pack_bf16(dh0v, dh1v);
                   }
                   store_sA(c0, o);
                   if (inner) stp(P.dsp, n, b, o);

@@ -479,7 +479,22 @@ __global__ void in_a_wgrad_kernel(int N, int H, const float* __restrict__ S, flo
 }
 
 __global__ void loss_finish_tc_kernel(const float* __restrict__ part, int n, float inv_total, float* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) { double s = 0.0; for (int i = 0; i < n; ++i) s += part[i]; out[0] = (float)(s * inv_total); }
+  // one warp; fixed summation tree (lane-strided partial sums in double, then a butterfly) -> deterministic
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 32) s += (double)part[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = (float)(s * inv_total);
+}
+
+// Variant B input-projection weight gradient without the B x (N E) x H GEMM: x_in[b, qE+e] = x_emb[bit_q(b)][e], so
+//   dWin[h, qE+e] = sum_b dh0[b,h] x_in[b,qE+e] = S[q, h] x_emb[0][e] + S[N+q, h] x_emb[1][e],   S = ind^T . dh0 (rows v N + q)
+// (S is computed anyway for the x_emb gradient).  Removes an 8.6 GFLOP GEMM and the 16 MB x_in gather at batch 8192.
+__global__ void in_b_wgrad_kernel(int N, int E, int H, const float* __restrict__ S, const float* __restrict__ x_emb, float* __restrict__ g_in_w) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)H * N * E) return;
+  const int h = (int)(i / (N * E)), j = (int)(i - (int64_t)h * N * E), q = j / E, e = j - q * E;
+  g_in_w[i] = S[(int64_t)q * H + h] * x_emb[e] + S[(int64_t)(N + q) * H + h] * x_emb[E + e];
 }
 
 // bias gradients: column sums of the bf16 dY arrays.  blockIdx.z splits the rows into chunks whose partial sums are added
@@ -730,7 +745,7 @@ static int launch_gemm(const HostOperand& A, const HostOperand& B, const TcGemm&
 // ---- workspace
 struct TcWs {
   // bf16 (element offsets into the bf16 region), fp32 (element offsets into the fp32 region)
-  int64_t xin, cond, ind, act, hL, dz, dgb, dh0, dlog, z1s, ss, h0s, dsp, gbh, dt, bf_total;
+  int64_t xin, cond, ind, act, hL, dz, dgb, dh0, dlog, d1s, hs, dsv, h0s, dsp, gbh, dt, bf_total;
   int64_t gb, h, z1, z2, logits, dres, S, loss_part, f_total;
 };
 static void tc_ws_layout(const ddqst_dims* d, int64_t B, TcWs* w) {
@@ -740,7 +755,7 @@ static void tc_ws_layout(const ddqst_dims* d, int64_t B, TcWs* w) {
   w->xin = take(B * N * E); w->cond = take(B * 2 * E); w->ind = take(B * 32); w->act = take(2 * L * B * H); w->hL = take(B * H);
   w->dz = take(2 * L * B * H); w->dgb = take(L * B * 2 * H); w->dh0 = take(B * H); w->dlog = take(B * 32);
   const int64_t priv = (B + 127) / 128 * 128 * H;     // one tile-private array of the fused pass (rows padded to whole tiles)
-  w->z1s = take(L * priv); w->ss = take(L * priv); w->h0s = take(priv); w->dsp = take(priv); w->gbh = take(L * 2 * priv); w->dt = take(H * 64);
+  w->d1s = take(L * priv); w->hs = take(L * priv); w->dsv = take(L * priv); w->h0s = take(priv); w->dsp = take(priv); w->gbh = take(L * 2 * priv); w->dt = take(H * 64);
   w->bf_total = off;
   off = 0;
   w->gb = take(L * B * 2 * H); w->h = take((L + 1) * B * H); w->z1 = take(L * B * H); w->z2 = take(L * B * H);
@@ -905,14 +920,15 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
     return g;
   };
 
-  gather_tc_kernel<<<(unsigned)B, 128, 0, s>>>(N, E, var_b ? params + pr.x_emb : nullptr, params + pr.time_emb, params + pr.basis_emb,
+  const bool fused = train_fused_enabled(B) && train_fused_supported(d);
+  // the fused pass builds h0 from the collapsed input table and gets dWin from S: it never needs the [B, N E] token-embedding matrix
+  gather_tc_kernel<<<(unsigned)B, 128, 0, s>>>(N, E, var_b && !fused ? params + pr.x_emb : nullptr, params + pr.time_emb, params + pr.basis_emb,
                                                xt, t, basis, xin, cond, ind);
   DDQST_LAUNCH_OK();
 
-  const bool fused = train_fused_enabled(B) && train_fused_supported(d);
   if (fused) {
     // ---------------------------------------------------------------- fused forward + data-gradient pass (train_fused.cuh)
-    __nv_bfloat16 *z1s = bf + w.z1s, *ss = bf + w.ss, *h0s = bf + w.h0s, *dsp = bf + w.dsp, *gbh = bf + w.gbh, *dt = bf + w.dt;
+    __nv_bfloat16 *d1s = bf + w.d1s, *hs = bf + w.hs, *dsv = bf + w.dsv, *h0s = bf + w.h0s, *dsp = bf + w.dsp, *gbh = bf + w.gbh, *dt = bf + w.dt;
     const int64_t priv = (B + 127) / 128 * 128 * H;
     // FiLM GEMMs inside the fused kernel when cond's K = 2E is a whole number of 128-column chunks and the embedding rows are 16-byte
     // aligned in the bf16 shadow; otherwise a separate launch writes the same tile-private arrays
@@ -937,7 +953,7 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
     P.head_b = params + pr.head_b; P.scale = loss_scale / (float)(B * N);
     P.film_kc = film_in_kernel ? (2 * E) / 128 : 0; P.E = E; P.t = t; P.basis = basis;
     P.temb = shadow + pr.time_emb; P.bemb = shadow + pr.basis_emb; P.film_b = params + pr.film_b[0]; P.film_b_stride = blk_stride;
-    P.dgb = dgb; P.dlog = dlog; P.z1s = z1s; P.ss = ss; P.h0s = h0s; P.dsp = dsp; P.priv_elems = priv;
+    P.dgb = dgb; P.dlog = dlog; P.d1s = d1s; P.hs = hs; P.dsv = dsv; P.h0s = h0s; P.dsp = dsp; P.priv_elems = priv;
     P.loss_part = loss_part;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DDQST_FT_DEBUG"); dbg = e ? atoi(e) : 0; } P.dbg = dbg; }
     switch (H) {
@@ -1054,7 +1070,7 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
       HostOperand Bo{cond, 1, 2 * E, B, 1, 2 * E, B * 2 * E, 0, 0};
       DDQST_TRY(grp.add(A, Bo, g, L));
     }
-    if (var_b) {  // Win
+    if (var_b && !fused) {  // Win (per-layer path; the fused path derives it from S below)
       TcGemm g = base_gemm(H, XIN, (int)B);
       g.o0 = grads + pr.in_w; g.ld = XIN;
       DDQST_TRY(grp.add(op_mn(dh0, H, B, H), op_mn(xin, XIN, B, XIN), g, 1));
@@ -1086,6 +1102,10 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
     const int chunks = (int)((B + 127) / 128 < 16 ? (B + 127) / 128 : 16);
     const int64_t per = (B + chunks - 1) / chunks;
     colsum_bf16_kernel<<<dim3((unsigned)((maxc + 63) / 64), (unsigned)n, (unsigned)chunks), 256, 0, s>>>(T, B, per);
+    DDQST_LAUNCH_OK();
+  }
+  if (var_b && fused) {
+    in_b_wgrad_kernel<<<(unsigned)(((int64_t)H * N * E + 255) / 256), 256, 0, s>>>(N, E, H, S, params + pr.x_emb, grads + pr.in_w);
     DDQST_LAUNCH_OK();
   }
   if (var_b) xemb_grad_kernel<<<dim3((unsigned)N, (unsigned)(H / 16)), 128, 0, s>>>(N, E, H, S, params + pr.in_w, grads + pr.x_emb);

@@ -213,15 +213,19 @@ def state_fidelity(target, rho) -> float:
             return x.to(dev).to(torch.complex128).contiguous()
         return torch.from_numpy(np.ascontiguousarray(np.asarray(getattr(x, "data", x), dtype=complex))).to(dev)
 
-    # a density matrix that is |psi><psi| (built from a vector, or Tr sigma^2 = 1 to rounding) takes the pure-target formula
-    for first, second in ((target, rho), (rho, target)):
-        if isinstance(first, DensityMatrix) or (not isinstance(first, Statevector) and np.ndim(getattr(first, "data", first)) == 2):
+    def is_vec(x):
+        return isinstance(x, Statevector) or (not isinstance(x, DensityMatrix) and np.ndim(getattr(x, "data", x)) == 1)
+
+    # two density matrices: one that is |psi><psi| (built from a vector, or Tr sigma^2 = 1 to rounding -- RQC/evaluate.py:71 wraps the
+    # clean state vector) takes the pure-target formula instead of two eigensolves.  The purity test costs a device sync, so it is
+    # only made when neither argument is a vector already.
+    if not is_vec(target) and not is_vec(rho):
+        for first, second in ((target, rho), (rho, target)):
             t, kind = _target_kind(first, dev)
             if kind == _lib.TARGET_STATEVECTOR:
                 return state_fidelity(Statevector(t.cpu().numpy()), second)
-            if kind == _lib.TARGET_RANK_ONE and not (isinstance(second, Statevector) or np.ndim(getattr(second, "data", second)) == 1):
-                other = as_dev(second)
-                return float(torch.sum(t * other.transpose(0, 1)).real.item())       # Tr(sigma rho)
+            if kind == _lib.TARGET_RANK_ONE:
+                return float(torch.sum(t * as_dev(second).transpose(0, 1)).real.item())       # Tr(sigma rho)
     a, b = as_dev(target), as_dev(rho)
     out = torch.zeros(1, dtype=torch.float64, device=dev)
     if a.dim() == 1 and b.dim() == 1:
