@@ -121,28 +121,47 @@ static int mlp_forward(const MlpCtx& c, const float* params, const uint16_t* x, 
   return launch_sgemm(g, c.s);
 }
 
-__global__ void mlp_init_bits_kernel(int64_t n, uint64_t seed, uint32_t basis, int64_t shot_offset, uint16_t* __restrict__ x) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Philox4 p = stream_block(seed, basis, 0, DDQST_SITE_INIT, (uint64_t)(shot_offset + i), 0);
-  x[i] = (uint16_t)(p.x & 1u);
+// ---- the notebook sampler as ONE launch.  The denoiser sees (x_t, t, basis) with x_t a single bit, so for a fixed basis its output
+// takes only 2 T distinct values: logits[t][x_t].  They are computed once, by the same forward kernels as before, on the 2 T rows
+// (x, t) = (0,1), (1,1), (0,2), ... -- and the T-step chain of NB c6:189-221 becomes a 2-state Markov chain per sample that never
+// leaves the registers: one thread per sample, the table in shared memory, Philox draws exactly as the per-step kernel of round 1 made them.
+// (Round 1 launched the gather + (num_hidden + 1) SGEMMs + the draw kernel for every step: 404 SGEMM and 240 elementwise launches
+// for T = 100.)  Same logits bit for bit -- every SGEMM output row depends on its own input row only -- hence the same samples.
+__global__ void mlp_table_inputs_kernel(int T, uint16_t* __restrict__ x, int32_t* __restrict__ t) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= 2 * T) return;
+  x[r] = (uint16_t)(r & 1);
+  t[r] = 1 + (r >> 1);
 }
 
-__global__ void mlp_reverse_step_kernel(int T, const float* __restrict__ sched, int t, int64_t n, uint64_t seed, uint32_t basis,
-                                        int64_t shot_offset, const float* __restrict__ logits, uint16_t* __restrict__ x) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float* lg = logits + i * 2;
-  x[i] = (uint16_t)reverse_step_bits(1, T, sched, DDQST_MODE_RENOISE, t, seed, basis, (uint64_t)(shot_offset + i), x[i],
-                                     [&](int, int cc) { return lg[cc]; });
-}
-
-__global__ void mlp_emit_kernel(const uint16_t* __restrict__ x, int64_t n, uint8_t* __restrict__ out, uint32_t* __restrict__ hist) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t v = x[i] & 1u;
-  if (out) out[i] = (uint8_t)v;
-  if (hist) atomicAdd(hist + v, 1u);
+__global__ void __launch_bounds__(256) mlp_chain_kernel(int T, const float* __restrict__ sched, const float* __restrict__ table, int64_t n,
+                                                        uint64_t seed, uint32_t basis, int64_t shot_offset, uint8_t* __restrict__ out,
+                                                        uint32_t* __restrict__ hist) {
+  extern __shared__ float s_tab[];                    // [2T][2] logits, then the schedule (betas[T+1], Q[T+1][4])
+  float* s_sched = s_tab + 4 * T;
+  for (int i = threadIdx.x; i < 4 * T; i += blockDim.x) s_tab[i] = table[i];
+  for (int i = threadIdx.x; i < 5 * (T + 1); i += blockDim.x) s_sched[i] = sched[i];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t ones = 0;
+  if (i < n) {
+    const uint64_t shot = (uint64_t)(shot_offset + i);
+    uint32_t x = stream_block(seed, basis, 0, DDQST_SITE_INIT, shot, 0).x & 1u;
+    for (int t = T; t >= 1; --t) {
+      const float* lg = s_tab + 4 * (t - 1) + 2 * x;
+      x = reverse_step_bits(1, T, s_sched, DDQST_MODE_RENOISE, t, seed, basis, shot, x, [&](int, int cc) { return lg[cc]; });
+    }
+    if (out) out[i] = (uint8_t)x;
+    ones = x;
+  }
+  if (hist) {
+    const uint32_t valid = __ballot_sync(0xFFFFFFFFu, i < n), set = __ballot_sync(0xFFFFFFFFu, ones != 0);
+    if ((threadIdx.x & 31) == 0) {
+      const uint32_t n1 = __popc(set), n0 = __popc(valid) - n1;
+      if (n0) atomicAdd(hist, n0);
+      if (n1) atomicAdd(hist + 1, n1);
+    }
+  }
 }
 
 }  // namespace ddqst
@@ -230,27 +249,23 @@ int ddqst_mlp_sample(const ddqst_mlp_dims* d, const float* params, const float* 
   if (n == 0) return DDQST_OK;
   DDQST_REQUIRE(n > 0 && params && sched, DDQST_EINVAL_SHAPE, "bad argument");
   DDQST_REQUIRE(basis_id >= 0 && basis_id < d->num_bases, DDQST_EINVAL_SHAPE, "basis_id=%d", basis_id);
-  const int64_t per = ddqst_mlp_workspace_bytes(d, 1);
-  if (per < 0) return DDQST_EINVAL_SHAPE;
-  int64_t chunk = n < 65536 ? n : 65536;
-  DDQST_REQUIRE(workspace && ws_bytes >= ddqst_mlp_workspace_bytes(d, chunk), DDQST_EWORKSPACE, "mlp_sample needs %lld workspace bytes",
-                (long long)ddqst_mlp_workspace_bytes(d, chunk));
-  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
-    const int64_t rows = n - r0 < chunk ? n - r0 : chunk;
-    MlpCtx c;
-    DDQST_TRY(mlp_ctx(&c, d, rows, workspace, ws_bytes, stream));
-    uint16_t* x = (uint16_t*)(c.dnext + align_up(rows * (d->hidden_dim > c.L.in_dim ? d->hidden_dim : c.L.in_dim), 64));
-    const unsigned gb = (unsigned)((rows + 255) / 256);
-    mlp_init_bits_kernel<<<gb, 256, 0, c.s>>>(rows, seed, (uint32_t)basis_id, shot_offset + r0, x);
-    DDQST_LAUNCH_OK();
-    for (int t = d->num_timesteps; t >= 1; --t) {
-      DDQST_TRY(mlp_forward(c, params, x, nullptr, t, nullptr, basis_id));
-      mlp_reverse_step_kernel<<<gb, 256, 0, c.s>>>(d->num_timesteps, sched, t, rows, seed, (uint32_t)basis_id, shot_offset + r0, c.logits, x);
-      DDQST_LAUNCH_OK();
-    }
-    mlp_emit_kernel<<<gb, 256, 0, c.s>>>(x, rows, out_bits ? out_bits + r0 : nullptr, out_hist);
-    DDQST_LAUNCH_OK();
-  }
+  const int T = d->num_timesteps;
+  const int64_t rows = 2 * (int64_t)T;
+  const int64_t ctx_bytes = ddqst_mlp_workspace_bytes(d, rows);
+  if (ctx_bytes < 0) return DDQST_EINVAL_SHAPE;
+  const int64_t need = ctx_bytes + align_up(rows * 2, 256) + align_up(rows * 4, 256);
+  DDQST_REQUIRE(workspace && ws_bytes >= need, DDQST_EWORKSPACE, "mlp_sample needs %lld workspace bytes, got %lld", (long long)need, (long long)ws_bytes);
+  MlpCtx c;
+  DDQST_TRY(mlp_ctx(&c, d, rows, workspace, ctx_bytes, stream));
+  uint16_t* x_rows = (uint16_t*)((char*)workspace + ctx_bytes);
+  int32_t* t_rows = (int32_t*)((char*)workspace + ctx_bytes + align_up(rows * 2, 256));
+  mlp_table_inputs_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, c.s>>>(T, x_rows, t_rows);
+  DDQST_LAUNCH_OK();
+  DDQST_TRY(mlp_forward(c, params, x_rows, t_rows, 0, nullptr, basis_id));            // logits[2T][2]: row 2 (t-1) + x
+  const size_t smem = sizeof(float) * (4 * (size_t)T + 5 * ((size_t)T + 1));
+  DDQST_REQUIRE(smem <= 48 * 1024, DDQST_EUNSUPPORTED, "num_timesteps=%d: the logit table does not fit shared memory", T);
+  mlp_chain_kernel<<<(unsigned)((n + 255) / 256), 256, smem, c.s>>>(T, sched, c.logits, n, seed, (uint32_t)basis_id, shot_offset, out_bits, out_hist);
+  DDQST_LAUNCH_OK();
   return DDQST_OK;
 }
 

@@ -152,7 +152,8 @@ class BitstringDDM:
         m = self.model
         _lib.check_index(int(basis_id), m.num_bases, "basis_id")
         out = torch.empty(num_samples, dtype=torch.uint8, device=self.device)
-        ws = _lib.workspace.get(lib.ddqst_mlp_workspace_bytes(C.byref(m.dims), min(num_samples, 65536)), self.device)
+        # scratch for the 2T-row logit table (the chain itself runs in registers: one launch for all samples and steps)
+        ws = _lib.workspace.get(lib.ddqst_mlp_workspace_bytes(C.byref(m.dims), 2 * self.num_timesteps) + 16 * self.num_timesteps + 1024, self.device)
         _lib.check(lib.ddqst_mlp_sample(C.byref(m.dims), _lib.ptr(m.flat_params), _lib.ptr(self._sched), int(basis_id), num_samples,
                                         shot_offset, self.seed, _lib.ptr(out), None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
         res = out.to(torch.int64)
