@@ -38,7 +38,7 @@ def main():
     dq._lib.load().ddqst_debug_train_path(mode)
     out = {"fused": mode}
     for name, dims, B in (("h128", (4, 81, 50, 32, 128, 2), 300), ("h256_ragged", (4, 81, 50, 32, 256, 2), 6200),
-                          ("c4", (8, 6561, 100, 128, 512, 4), 1024), ("c5", (10, 59049, 100, 128, 512, 4), 1000),
+                          ("c4", (8, 6561, 100, 128, 512, 4), 1024), ("c4_b4200", (8, 6561, 100, 128, 512, 4), 4200), ("c5", (10, 59049, 100, 128, 512, 4), 1000),
                           ("variantA", (3, 27, 100, 64, 512, 4), 256)):
         torch.manual_seed(0)
         variant = "A" if name == "variantA" else "B"

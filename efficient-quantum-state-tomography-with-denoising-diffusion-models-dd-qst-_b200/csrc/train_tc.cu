@@ -34,7 +34,7 @@ constexpr int kFtBatches = kFtColsPerWarp / 16;
 constexpr int kFtThreads = kFtEpiThreads + 64;   // + warp 8 (TMA) + warp 9 (MMA, TMEM alloc).  10 warps = at most 3 per SM sub-partition,
                                                  // so ptxas may use 168 registers per thread (a 16 + 2-warp layout is capped at 96 and spilled
                                                  // ~500 B per thread into local memory, which misses L1 here: shared memory takes the carve-out)
-template <int BN> __host__ __device__ constexpr int gt_stages() { return BN <= 64 ? 8 : 6; }
+template <int BN> __host__ __device__ constexpr int gt_stages() { return BN <= 64 ? 8 : (BN <= 128 ? 6 : 4); }
 constexpr int kGtMaxZ = 32;
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
@@ -727,7 +727,7 @@ struct GroupBuilder {
     DDQST_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_group_kernel<BN>, grp));
     return DDQST_OK;
   }
-  int launch(cudaStream_t s) { return bn == 128 ? launch_bn<128>(s) : launch_bn<64>(s); }
+  int launch(cudaStream_t s) { return bn == 256 ? launch_bn<256>(s) : (bn == 128 ? launch_bn<128>(s) : launch_bn<64>(s)); }
 };
 
 // BN = 128 when the grid still covers the machine (or N is not a multiple of 64-wide tiles anyway), else 64
@@ -1039,6 +1039,13 @@ static int train_tc_run(const ddqst_dims* d, const float* params, const __nv_bfl
       static int thr = -1;
       if (thr < 0) { const char* e = getenv("DDQST_TC_GROUP_BN128_BATCH"); thr = e ? atoi(e) : 1024; }
       if (B >= thr && E % 32 == 0) grp.bn = 128;
+      // 128 x 256 tiles (DDQST_TC_GROUP_BN256_BATCH=<batch>): built and measured equal to 128 x 128 at batch 8192 (0.569 vs 0.574 ms per step).
+      // The grouped launch moves ~1 GB of operands through L2 per step at that batch (every CTA re-reads its A and B panels), i.e. it is
+      // L2-bandwidth-bound chip-wide; wider single-CTA tiles trade traffic for fewer CTAs.  Cutting it needs cluster multicast of the
+      // shared panels -- left for later; off by default.
+      static int thr256 = -1;
+      if (thr256 < 0) { const char* e = getenv("DDQST_TC_GROUP_BN256_BATCH"); thr256 = e ? atoi(e) : (1 << 30); }
+      if (B >= thr256 && E % 128 == 0 && H % 256 == 0) grp.bn = 256;
       static int sk = -1;
       // measured at batch 8192 (step 0.584 ms without, 0.618 ms with): the atomic epilogues cost more than the better wave
       // balance returns, so split-K stays an opt-in (DDQST_TC_SPLIT_K=1)
