@@ -11,7 +11,8 @@ for N, shots in ((6, 100000), (8, 1000000), (8, 10000)):
     h = dq.born_histograms(psi, N, shots, seed=1)
     raw = dq.linear_inversion_raw(h, N)
     dim = 1 << N
-    ws = torch.zeros(2 * 16 * dim * dim + 8 * dim + 4096, dtype=torch.uint8, device="cuda")
+    extra = 0 if os.environ.get('NO_EXTRA') else 24 * dim * dim
+    ws = torch.zeros(2 * 16 * dim * dim + 8 * dim + 1024 + extra, dtype=torch.uint8, device="cuda")
     t = raw.clone()
     dq._lib.check(lib.ddqst_psd_project(dq._lib.ptr(t), dim, None, dq._lib.ptr(ws), ws.numel(), dq._lib.stream_ptr()))
     torch.cuda.synchronize()

@@ -1187,6 +1187,8 @@ static int launch_jacobi_cluster(double2* GT, int n, int max_sweeps, double tol,
 
 // Hermitian eigendecomposition of A[n,n] (n a power of two >= 2): evals[n], VT (rows = eigenvectors).
 // ws: GT[n*n] double2, then JacobiCtl.
+#include "eig_mixed.cuh"
+
 // stop_ratio2: see JacobiCtl.  The eigenvalue problem is solved on A + sigma I (sigma = 2 ||A||_F), so a relative off-diagonal
 // |gamma| / sqrt(a b) = r between two columns whose eigenvalues differ by `gap` means an eigenvector mixing of r sigma / (2 gap):
 // 1e-7 is ample for rho itself; the mixed-state fidelity (square roots of a rank-deficient spectrum) asks for 1e-12.
@@ -1194,7 +1196,9 @@ static int launch_jacobi_cluster(double2* GT, int n, int max_sweeps, double tol,
 // N = 6 / 8 (benchmarks/jacobi_sweeps.py) the sweep after such a start leaves 1e-11 .. 8e-9 -- three orders below the 1e-5 bar on rho --
 // and it saves one of nine sweeps against the round-1 threshold of 1e-7.  (The sweep count itself is the cyclic method's: a slow, roughly
 // halving phase over sweeps 2-7 while the 250 clustered noise eigenvalues separate; a 40x smaller shift does not shorten it.)
-static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char* ws, cudaStream_t s, float stop_ratio2 = 1e-11f) {
+// extra / extra_bytes: optional scratch of 24 n^2 bytes; when present (and 64 <= n <= 256) the sweeps start in fp32 (eig_mixed.cuh).
+static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char* ws, cudaStream_t s, float stop_ratio2 = 1e-11f,
+                       char* extra = nullptr, int64_t extra_bytes = 0) {
   double2* GT = (double2*)ws;
   JacobiCtl* ctl = (JacobiCtl*)(ws + (int64_t)16 * n * n);
   static double shift_scale = -1.0;
@@ -1204,6 +1208,49 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
   int max_sweeps = 60;
   double tol = 1e-15;
   bool ring_done = false;
+  static int mixed_env = -1;
+  if (mixed_env < 0) { const char* e = getenv("DDQST_JACOBI_MIXED"); mixed_env = (e && e[0] == '0') ? 0 : 1; }
+  const int64_t nn = (int64_t)n * n;
+  if (mixed_env == 1 && extra && extra_bytes >= 24 * nn && n >= 64 && n <= 256) {
+    double2* X1 = (double2*)extra;
+    float2* G32 = (float2*)(extra + 16 * nn);
+    eig_to_f32_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(GT, G32, nn);
+    DDQST_LAUNCH_OK();
+    // fp32 sweeps stop once a sweep STARTS below 1e-5 relative off-diagonal (ratio^2 < 1e-10; fp32 resolves ~1e-6): that carries the
+    // solve through the slow phase, and the fp64 kernel then needs 2 sweeps
+    bool f32_done = false;
+    {
+      JacobiCtl* c32 = ctl;                     // same control block; its stop threshold is rewritten below for the fp64 phase
+      // set the fp32 stop threshold (init wrote the fp64 one)
+      eig_set_stop_kernel<<<1, 32, 0, s>>>(c32, 1e-10f);
+      DDQST_LAUNCH_OK();
+      const int epl = n / 32;
+      switch (epl) {
+        case 2: DDQST_TRY(launch_jacobi_oddeven_f32<2>(G32, n, 20, 1e-7f, c32, s, &f32_done)); break;
+        case 4: DDQST_TRY(launch_jacobi_oddeven_f32<4>(G32, n, 20, 1e-7f, c32, s, &f32_done)); break;
+        default: DDQST_TRY(launch_jacobi_oddeven_f32<8>(G32, n, 20, 1e-7f, c32, s, &f32_done)); break;
+      }
+    }
+    if (f32_done) {
+      dim3 grid((n + 15) / 16, (n + 15) / 16), blk(16, 16);
+      eig_normalise_rows_kernel<<<n, 128, 0, s>>>(G32, n, VT, ctl, stop_ratio2);          // R (rows = eigenvector estimates), ctl reset
+      DDQST_LAUNCH_OK();
+      // two Newton-Schulz steps: the fp32 columns are orthogonal to ~1e-5 x sqrt(n), one step leaves ~1e-7 (measured: 2e-6 in the
+      // eigenvalues), the second ~1e-14
+      eig_zgemm_kernel<0><<<grid, blk, 0, s>>>(VT, VT, nullptr, n, ctl, X1);               // M = R R^H
+      DDQST_LAUNCH_OK();
+      eig_zgemm_kernel<1><<<grid, blk, 0, s>>>(X1, VT, VT, n, ctl, GT);                    // R1 = 1.5 R - 0.5 M R   (into the GT buffer)
+      DDQST_LAUNCH_OK();
+      eig_zgemm_kernel<0><<<grid, blk, 0, s>>>(GT, GT, nullptr, n, ctl, X1);               // M1 = R1 R1^H
+      DDQST_LAUNCH_OK();
+      eig_zgemm_kernel<1><<<grid, blk, 0, s>>>(X1, GT, GT, n, ctl, VT);                    // R2 = 1.5 R1 - 0.5 M1 R1 (into the VT buffer)
+      DDQST_LAUNCH_OK();
+      DDQST_CUDA_OK(cudaMemcpyAsync(GT, VT, 16 * nn, cudaMemcpyDeviceToDevice, s));
+      eig_zgemm_kernel<2><<<grid, blk, 0, s>>>(GT, A, nullptr, n, ctl, X1);                // G = A' R'^T as rows: X1[j][:] = A' v_j
+      DDQST_LAUNCH_OK();
+      GT = X1;                                                                            // the fp64 sweeps and the read-out work on X1
+    }
+  }
   const char* ring_env = getenv("DDQST_JACOBI_RING");          // DDQST_JACOBI_RING=0 keeps the L2-resident kernel (debugging aid)
   if (ring_env == nullptr || ring_env[0] != '0') {
     if (n <= 256 && (ring_env == nullptr || ring_env[0] != '1')) {      // DDQST_JACOBI_RING=1 forces the two-column ring
@@ -1389,7 +1436,8 @@ int ddqst_psd_project(double* rho, int32_t dim, double* evals_out, void* workspa
   double2* VT = (double2*)ws;
   char* jws = ws + 16 * nn;                                  // GT + ctl
   double* evals = (double*)(jws + 16 * nn + 512);
-  DDQST_TRY(jacobi_eigh((const double2*)rho, dim, evals, VT, jws, s));
+  char* extra = ws_bytes >= need + 24 * nn ? ws + need : nullptr;        // optional: lets the sweeps start in fp32 (eig_mixed.cuh)
+  DDQST_TRY(jacobi_eigh((const double2*)rho, dim, evals, VT, jws, s, 1e-11f, extra, extra ? 24 * nn : 0));
   clip_normalise_kernel<<<1, 256, 0, s>>>(evals, dim);
   DDQST_LAUNCH_OK();
   dim3 grid((dim + 15) / 16, (dim + 15) / 16);
@@ -1415,7 +1463,8 @@ int ddqst_fidelity_mixed(const double* rho_a, const double* rho_b, int32_t dim, 
   char* jws = ws + 48 * nn;                    // GT (16nn) + ctl
   double* evals = (double*)(jws + 16 * nn + 512);
   dim3 grid((dim + 15) / 16, (dim + 15) / 16), blk(16, 16);
-  DDQST_TRY(jacobi_eigh((const double2*)rho_a, dim, evals, VT, jws, s));
+  char* extra = ws_bytes >= need + 24 * nn ? ws + need : nullptr;              // optional: fp32 start of the sweeps (eig_mixed.cuh)
+  DDQST_TRY(jacobi_eigh((const double2*)rho_a, dim, evals, VT, jws, s, 1e-11f, extra, extra ? 24 * nn : 0));
   rebuild_kernel<<<grid, blk, 0, s>>>(VT, evals, dim, 1, S);                    // sqrt(a), negatives clipped
   DDQST_LAUNCH_OK();
   zgemm_kernel<<<grid, blk, 0, s>>>(S, (const double2*)rho_b, dim, Tm);         // sqrt(a) b
@@ -1423,7 +1472,7 @@ int ddqst_fidelity_mixed(const double* rho_a, const double* rho_b, int32_t dim, 
   zgemm_kernel<<<grid, blk, 0, s>>>(Tm, S, dim, VT);                            // M = sqrt(a) b sqrt(a) (reuse VT storage)
   DDQST_LAUNCH_OK();
   DDQST_CUDA_OK(cudaMemcpyAsync(Tm, VT, 16 * nn, cudaMemcpyDeviceToDevice, s));
-  DDQST_TRY(jacobi_eigh(Tm, dim, evals, VT, jws, s, 1e-24f));
+  DDQST_TRY(jacobi_eigh(Tm, dim, evals, VT, jws, s, 1e-24f, extra, extra ? 24 * nn : 0));
   DDQST_TRY(launch_rayleigh(Tm, VT, dim, evals, s));
   sqrt_sum_sq_kernel<<<1, 256, 0, s>>>(evals, dim, out);
   DDQST_LAUNCH_OK();
@@ -1457,7 +1506,8 @@ int ddqst_recon_report(double* rho, int32_t num_qubits, const double* target, in
   int rgrid = (int)((nn + 255) / 256);
   if (rgrid > num_sms() * 4) rgrid = num_sms() * 4;
   if (dim >= 2) {
-    DDQST_TRY(jacobi_eigh((const double2*)rho, dim, evals, VT, jws, s));
+    char* extra = ws_bytes >= need + 24 * nn ? ws + need : nullptr;      // optional: lets the sweeps start in fp32 (eig_mixed.cuh)
+    DDQST_TRY(jacobi_eigh((const double2*)rho, dim, evals, VT, jws, s, 1e-11f, extra, extra ? 24 * nn : 0));
     clip_normalise_kernel<<<1, 256, 0, s>>>(evals, dim);
     DDQST_LAUNCH_OK();
     rebuild_kernel<<<grid, blk, 0, s>>>(VT, evals, dim, 0, (double2*)rho);
@@ -1482,7 +1532,8 @@ int ddqst_recon_report(double* rho, int32_t num_qubits, const double* target, in
     DDQST_LAUNCH_OK();
     zgemm_kernel<<<grid, blk, 0, s>>>(tmp, S, dim, M);
     DDQST_LAUNCH_OK();
-    DDQST_TRY(jacobi_eigh(M, dim, evals2, tmp, jws, s, 1e-24f));
+    char* extra2 = ws_bytes >= need + 24 * nn ? ws + need : nullptr;
+    DDQST_TRY(jacobi_eigh(M, dim, evals2, tmp, jws, s, 1e-24f, extra2, extra2 ? 24 * nn : 0));
     DDQST_TRY(launch_rayleigh(M, tmp, dim, evals2, s));
     sqrt_sum_sq_kernel<<<1, 256, 0, s>>>(evals2, dim, report);
     DDQST_LAUNCH_OK();
@@ -1518,7 +1569,8 @@ int ddqst_metrics(const double* rho, int32_t num_qubits, double* out, void* work
   if (grid > num_sms() * 4) grid = num_sms() * 4;
   purity_kernel<<<grid, 256, 0, s>>>((const double2*)rho, dim, out);
   DDQST_LAUNCH_OK();
-  DDQST_TRY(jacobi_eigh((const double2*)rho, dim, evals, VT, jws, s));
+  char* extra = ws_bytes >= need + 24 * nn ? ws + need : nullptr;
+  DDQST_TRY(jacobi_eigh((const double2*)rho, dim, evals, VT, jws, s, 1e-11f, extra, extra ? 24 * nn : 0));
   entropy_kernel<<<1, 256, 0, s>>>(evals, dim, out + 1);
   DDQST_LAUNCH_OK();
   const int cut = num_qubits / 2;

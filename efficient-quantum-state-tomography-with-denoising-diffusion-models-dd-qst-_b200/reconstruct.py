@@ -173,7 +173,7 @@ def make_positive_semidefinite(rho) -> DensityMatrix:
     dim = t.shape[0]
     if dim == 1:
         return DensityMatrix(t)
-    nbytes = 2 * 16 * dim * dim + 8 * dim + 4096
+    nbytes = 2 * 16 * dim * dim + 8 * dim + 1024 + 24 * dim * dim + 4096      # + 24 n^2: lets the eigensolver start its sweeps in fp32
     ws = _lib.workspace.get(nbytes, t.device)
     _lib.check(lib.ddqst_psd_project(_lib.ptr(t), dim, None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     return DensityMatrix(t)
@@ -235,7 +235,7 @@ def state_fidelity(target, rho) -> float:
         _lib.check(lib.ddqst_fidelity_pure(_lib.ptr(psi), _lib.ptr(mat), mat.shape[0], _lib.ptr(out), _lib.stream_ptr()))
         return float(out.item())
     dim = a.shape[0]
-    ws = _lib.workspace.get(5 * 16 * dim * dim + 8 * dim + 4096, dev)
+    ws = _lib.workspace.get(5 * 16 * dim * dim + 8 * dim + 1024 + 24 * dim * dim + 4096, dev)
     _lib.check(lib.ddqst_fidelity_mixed(_lib.ptr(a), _lib.ptr(b), dim, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     return float(out.item())
 
@@ -246,7 +246,7 @@ def get_metrics(rho, num_qubits: int):
     t = DensityMatrix(rho).device_tensor()
     dim = t.shape[0]
     out = torch.zeros(3, dtype=torch.float64, device=t.device)
-    ws = _lib.workspace.get(3 * 16 * dim * dim + 8 * dim + 4096, t.device)
+    ws = _lib.workspace.get(3 * 16 * dim * dim + 8 * dim + 1024 + 24 * dim * dim + 4096, t.device)
     _lib.check(lib.ddqst_metrics(_lib.ptr(t), num_qubits, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     p, s, e = out.cpu().tolist()
     return p, s, e
@@ -300,7 +300,7 @@ def recon_report(data, num_qubits: int, target=None, convention: str = "reversed
     tgt, kind = _target_kind(target, dev)
     evals = torch.empty(dim, dtype=torch.float64, device=dev)
     report = torch.empty(5, dtype=torch.float64, device=dev)
-    nbytes = (5 if kind == _lib.TARGET_MIXED else 3) * 16 * dim * dim + 16 * dim + 2048
+    nbytes = (5 if kind == _lib.TARGET_MIXED else 3) * 16 * dim * dim + 16 * dim + 2048 + 24 * dim * dim     # + 24 n^2: fp32 start of the sweeps
     ws = _lib.workspace.get(nbytes, dev)
     _lib.check(lib.ddqst_recon_report(_lib.ptr(rho), num_qubits, _lib.ptr(tgt), kind, _lib.ptr(evals), _lib.ptr(report),
                                       _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
