@@ -21,6 +21,14 @@ __device__ __forceinline__ void jr_send_f(uint32_t raddr, float2 v, uint32_t rba
                ::"r"(raddr), "f"(v.x), "f"(v.y), "r"(rbar) : "memory");
 }
 
+__device__ __forceinline__ void jr_send_f4(uint32_t raddr, float2 u, float2 v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(raddr), "f"(u.x), "f"(u.y), "f"(v.x), "f"(v.y), "r"(rbar) : "memory");
+}
+// element e of a lane's column slice sits at row (e >> 1) * 64 + 2 * lane + (e & 1): rows come in adjacent PAIRS, so a lane moves
+// 16 bytes per st.async / LDS / LDG (half the instructions of the 8-byte form; the st.async issue rate bounds the exchange)
+__device__ __forceinline__ int jr_row_f(int lane, int e) { return (e >> 1) * 64 + 2 * lane + (e & 1); }
+
 template <int EPL>
 __global__ void __launch_bounds__(kJcThreads) jacobi_oddeven_f32_kernel(float2* __restrict__ GT, int n, int max_sweeps, float tol,
                                                                         JacobiCtl* ctl) {
@@ -49,7 +57,7 @@ __global__ void __launch_bounds__(kJcThreads) jacobi_oddeven_f32_kernel(float2* 
   float2 a[EPL], b[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) {
-    const int i = lane + 32 * e;
+    const int i = jr_row_f(lane, e);
     const bool ok = active && i < n;
     a[e] = ok ? GT[(int64_t)(2 * k) * n + i] : make_float2(0.f, 0.f);
     b[e] = ok ? GT[(int64_t)(2 * k + 1) * n + i] : make_float2(0.f, 0.f);
@@ -111,10 +119,10 @@ __global__ void __launch_bounds__(kJcThreads) jacobi_oddeven_f32_kernel(float2* 
         if (!odd) {
           if (k >= 1) {
 #pragma unroll
-            for (int e = 0; e < EPL; ++e) { const int i = lane + 32 * e; if (i < n) jr_send_f(left_addr + (uint32_t)i * 8u, a[e], left_bar); }
+            for (int e = 0; e < EPL; e += 2) { const int i = jr_row_f(lane, e); if (i < n) jr_send_f4(left_addr + (uint32_t)i * 8u, a[e], a[e + 1], left_bar); }
           } else {
 #pragma unroll
-            for (int e = 0; e < EPL; ++e) { const int i = lane + 32 * e; if (i < n) *reinterpret_cast<float2*>(park + i * 8) = a[e]; }
+            for (int e = 0; e < EPL; e += 2) { const int i = jr_row_f(lane, e); if (i < n) *reinterpret_cast<float4*>(park + i * 8) = make_float4(a[e].x, a[e].y, a[e + 1].x, a[e + 1].y); }
           }
 #pragma unroll
           for (int e = 0; e < EPL; ++e) a[e] = b[e];
@@ -122,14 +130,14 @@ __global__ void __launch_bounds__(kJcThreads) jacobi_oddeven_f32_kernel(float2* 
             mbar_wait(bar(warp, 1), (g >> 1) & 1u, 64);
             const uint8_t* in = jr_smem + (warp * 3 + 1) * COLB;
 #pragma unroll
-            for (int e = 0; e < EPL; ++e) { const int i = lane + 32 * e; if (i < n) b[e] = *reinterpret_cast<const float2*>(in + i * 8); }
+            for (int e = 0; e < EPL; e += 2) { const int i = jr_row_f(lane, e); if (i < n) { const float4 v = *reinterpret_cast<const float4*>(in + i * 8); b[e] = make_float2(v.x, v.y); b[e + 1] = make_float2(v.z, v.w); } }
             __syncwarp();
             if (lane == 0) mbar_expect_tx(bar(warp, 1), colbytes);
           }
         } else {
           if (k <= h - 2) {
 #pragma unroll
-            for (int e = 0; e < EPL; ++e) { const int i = lane + 32 * e; if (i < n) jr_send_f(right_addr + (uint32_t)i * 8u, b[e], right_bar); }
+            for (int e = 0; e < EPL; e += 2) { const int i = jr_row_f(lane, e); if (i < n) jr_send_f4(right_addr + (uint32_t)i * 8u, b[e], b[e + 1], right_bar); }
           }
 #pragma unroll
           for (int e = 0; e < EPL; ++e) b[e] = a[e];
@@ -137,13 +145,13 @@ __global__ void __launch_bounds__(kJcThreads) jacobi_oddeven_f32_kernel(float2* 
             mbar_wait(bar(warp, 0), (g >> 1) & 1u, 65);
             const uint8_t* in = jr_smem + (warp * 3 + 0) * COLB;
 #pragma unroll
-            for (int e = 0; e < EPL; ++e) { const int i = lane + 32 * e; if (i < n) a[e] = *reinterpret_cast<const float2*>(in + i * 8); }
+            for (int e = 0; e < EPL; e += 2) { const int i = jr_row_f(lane, e); if (i < n) { const float4 v = *reinterpret_cast<const float4*>(in + i * 8); a[e] = make_float2(v.x, v.y); a[e + 1] = make_float2(v.z, v.w); } }
             __syncwarp();
             if (lane == 0) mbar_expect_tx(bar(warp, 0), colbytes);
           } else {
             __syncwarp();
 #pragma unroll
-            for (int e = 0; e < EPL; ++e) { const int i = lane + 32 * e; if (i < n) a[e] = *reinterpret_cast<const float2*>(park + i * 8); }
+            for (int e = 0; e < EPL; e += 2) { const int i = jr_row_f(lane, e); if (i < n) { const float4 v = *reinterpret_cast<const float4*>(park + i * 8); a[e] = make_float2(v.x, v.y); a[e + 1] = make_float2(v.z, v.w); } }
           }
         }
       }
@@ -158,7 +166,7 @@ __global__ void __launch_bounds__(kJcThreads) jacobi_oddeven_f32_kernel(float2* 
   if (active) {
 #pragma unroll
     for (int e = 0; e < EPL; ++e) {
-      const int i = lane + 32 * e;
+      const int i = jr_row_f(lane, e);
       if (i < n) { GT[(int64_t)(2 * k) * n + i] = a[e]; GT[(int64_t)(2 * k + 1) * n + i] = b[e]; }
     }
   }
