@@ -16,6 +16,12 @@
 #pragma once
 // (included inside namespace ddqst)
 
+// DDQST_PAIR_LD32=1: fetch a warp's 32 accumulator columns of a chunk with one tcgen05.ld.x32 instead of two .x16 (one TMEM round trip
+// per chunk).  Measured in round 2: 2.75 M bitstrings/s against 2.76-2.83 M -- no gain (the kernel is power-capped: shorter stalls turn
+// into lower clocks) and 144 B more spills per thread, so it stays off.
+#ifndef DDQST_PAIR_LD32
+#define DDQST_PAIR_LD32 0
+#endif
 constexpr int kRing2 = 4;                 // stages of 16 KB per CTA
 
 template <int H>
@@ -340,11 +346,20 @@ sampler_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           for (int n = 0; n < NCH; ++n) {
             wait_acc(n, 9);
             const int c0 = n * 128 + cs * 32;
+#if DDQST_PAIR_LD32
+            uint32_t rr[32];                          // both 16-column batches of the warp's slice in ONE tcgen05.ld: one TMEM round trip per chunk
+            tmem_ld32(t_lane + c0, rr);
+            tmem_wait_ld32(rr);
+#endif
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
+#if DDQST_PAIR_LD32
+              const uint32_t* r = rr + 16 * b;
+#else
               uint32_t r[16];
               tmem_ld16(t_lane + c0 + b * 16, r);
               tmem_wait_ld16(r);
+#endif
               uint32_t o[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -367,11 +382,20 @@ sampler_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           for (int n = 0; n < NCH; ++n) {
             wait_acc(n, 10);
             const int c0 = n * 128 + cs * 32;
+#if DDQST_PAIR_LD32
+            uint32_t rr[32];
+            tmem_ld32(t_lane + c0, rr);
+            tmem_wait_ld32(rr);
+#endif
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
+#if DDQST_PAIR_LD32
+              const uint32_t* r = rr + 16 * b;
+#else
               uint32_t r[16];
               tmem_ld16(t_lane + c0 + b * 16, r);
               tmem_wait_ld16(r);
+#endif
               uint32_t o[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
