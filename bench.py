@@ -13,7 +13,7 @@ weak-scaled (every rank samples its own bases, no collective: SURVEY 8e); `e2e` 
                 counts -> linear inversion -> PSD -> fidelity, timed end to end on every N (strong scaling, collective inside)
   train_step    C4 and C5 models, 1024 samples per GPU, CUDA-graph replay; for N > 1 data parallel with the NCCL gradient
                 all-reduce captured inside the graph, every rank stepping
-  recon_fidelity, c5, eager_b200, cpu_baseline (see DESIGN.md section 9).
+  recon_fidelity, c5, eager_b200, cpu_baseline (see DESIGN.md section 8).
 
 Reference arm.  Imports nothing of this repo's package: the reference's own `ConditionalD3PM` + `DiscreteDiffusion.p_sample`
 (RQC/model.py:27, RQC/diffusion.py:53) from the verbatim copy in oracle/_ref (oracle/make_ref.py), torch CPU, all host threads;

@@ -13,15 +13,19 @@
 //   A operand  the activation / gradient tile, written by the 16 epilogue warps straight into shared memory in the UMMA
 //              K-major 128B-swizzled layout; the next GEMM starts on chunk n as soon as chunk n is published (chunk
 //              pipelining, see sampler_pair.cuh), so the tensor pipe works under the epilogue.
-//   epilogues  forward: bias, FiLM h(1+gamma)+beta, SiLU, residual (stream kept in registers as bf16x2), head: softmax
+//   epilogues  forward: FiLM GEMM + bias -> gamma|beta, bias, FiLM h(1+gamma)+beta, SiLU, residual, head: softmax
 //              cross-entropy + dlogits;  backward: silu'(z1), silu'(s), FiLM backward (dgamma = da*h, dbeta = da,
-//              dh += da(1+gamma)), residual gradient in registers.
+//              dh += da(1+gamma)); the residual stream / residual gradient are re-read from tile-private saves, not kept in registers.
 //
 // What leaves the SM pair, once, as bf16 (the operands of the weight-gradient GEMMs, which reduce over the batch and
 // therefore stay a separate grouped launch): a_l, u_l, h_L, dz1_l, dz2_l, dgamma|dbeta_l, dh_0, dlogits; plus what the
-// backward half re-reads (z1_l, s_l = pre-activation of h_{l+1}, h_0).  No fp32 activation round trips.
+// backward half re-reads (silu'(z1_l), h_{l+1}, silu'(s_l), h_0, gamma|beta -- in a tile-private coalesced layout).  No fp32 activation
+// round trips.
 //
-// GEMM sequence per tile (4L+3): input (K=32 hi/lo table), [W1_l, W2_l] l=0..L-1, head, head^T, [W2_l^T, W1_l^T] l=L-1..0.
+// GEMM sequence per tile (6L+3 with the FiLM phase in-kernel, else 4L+3): [Wfilm_l gamma half, beta half] l=0..L-1 (K = 2E, A = the gathered
+// cond tile), input (K=32 hi/lo table), [W1_l, W2_l] l=0..L-1, head, head^T, [W2_l^T, W1_l^T] l=L-1..0.
+// Debug aids: DDQST_FT_DEBUG bit 0 = clock stamps (ddqst_debug_ft_stamps), bits 1-4 switch off the bulk stores / tile-private stores /
+// per-row dgamma|dbeta stores / tile-private loads (timing ablations only: results are wrong with them set).
 #pragma once
 
 // kFtEpiWarps / kFtEpiThreads / kFtColsPerWarp / kFtBatches / kFtThreads: see train_tc.cu (the FiLM GEMM epilogue writes the
