@@ -23,6 +23,8 @@ SOURCES = ["api.cu", "simt.cu", "recon.cu", "eig.cu", "sampler_tc.cu", "train.cu
            "dataset.cu", "synth.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# developer builds: DDQST_NVCC_DEFINES="DDQST_JL_PROFILE ..." adds -D switches (part of the content hash like every other flag)
+NVCC_FLAGS += ["-D" + d for d in os.environ.get("DDQST_NVCC_DEFINES", "").split()]
 
 
 def _nvcc() -> str:

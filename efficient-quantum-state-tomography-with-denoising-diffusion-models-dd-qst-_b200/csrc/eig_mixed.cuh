@@ -223,6 +223,8 @@ __global__ void eig_normalise_rows_kernel(const float2* __restrict__ G32, int n,
   const double inv = a > 0.0 ? 1.0 / sqrt(a) : 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) { const float2 v = G32[(int64_t)j * n + i]; R[(int64_t)j * n + i] = make_double2(v.x * inv, v.y * inv); }
   if (j == 0 && threadIdx.x == 0) {
+    ctl->f32_sweeps = ctl->sweeps_done;
+    ctl->f32_last_ratio2 = ctl->sweeps_done >= 1 && ctl->sweeps_done <= 48 ? __uint_as_float(ctl->max_ratio2[ctl->sweeps_done - 1]) : 0.f;
     ctl->sweeps_done = 0;
     ctl->stop_ratio2 = stop_ratio2;
     for (int i = 0; i < 64; ++i) ctl->rotations[i] = 0;

@@ -395,28 +395,39 @@ struct JacobiCtl {            // lives in the 512 bytes between G and the eigenv
   int sweeps_done;
   unsigned int max_ratio2[48];     // ring kernel: per sweep, float bits of max |gamma|^2 / (a b) seen BEFORE rotating
   float stop_ratio2;               // a sweep that starts with every |gamma|^2 / (a b) below this is the last one
+  int f32_sweeps;                  // mixed-precision solve: sweeps the fp32 phase took, and the worst ratio its last sweep started with
+  float f32_last_ratio2;
 };
 static_assert(sizeof(JacobiCtl) <= 512, "JacobiCtl must fit the gap in the eigensolver workspace");
 
-__global__ void jacobi_init_kernel(const double2* __restrict__ A, int n, double2* __restrict__ GT, JacobiCtl* ctl, float stop_ratio2,
-                                   double shift_scale) {
-  // single block: Frobenius norm -> sigma, then GT = columns of A + sigma I.  The eigenvector matrix is never
-  // accumulated: at convergence G = A'V has orthogonal columns lambda'_j v_j with lambda'_j >= sigma/2 > 0, so
-  // v_j = g_j / ||g_j|| (jacobi_evals_kernel) -- half the rotation work and memory traffic of tracking V.
+// Frobenius norm in per-block partial sums (summed in a fixed order by every block of jacobi_init_kernel: deterministic sigma)
+__global__ void __launch_bounds__(256) jacobi_norm_kernel(const double2* __restrict__ A, int64_t total, double* __restrict__ partial) {
   __shared__ double scratch[96];
   double f = 0.0, z1 = 0.0, z2 = 0.0;
-  const int64_t total = (int64_t)n * n;
-  for (int64_t e = threadIdx.x; e < total; e += blockDim.x) { double2 v = A[e]; f += v.x * v.x + v.y * v.y; }
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) { const double2 v = A[e]; f += v.x * v.x + v.y * v.y; }
   block_sum3(f, z1, z2, scratch);
+  if (threadIdx.x == 0) partial[blockIdx.x] = f;
+}
+
+__global__ void __launch_bounds__(256) jacobi_init_kernel(const double2* __restrict__ A, int n, double2* __restrict__ GT, JacobiCtl* ctl,
+                                                          float stop_ratio2, double shift_scale, const double* __restrict__ partial, int nparts) {
+  // sigma from the Frobenius norm, then GT = columns of A + sigma I.  The eigenvector matrix is never
+  // accumulated: at convergence G = A'V has orthogonal columns lambda'_j v_j with lambda'_j >= sigma/2 > 0, so
+  // v_j = g_j / ||g_j|| (jacobi_evals_kernel) -- half the rotation work and memory traffic of tracking V.
+  double f = 0.0;
+  for (int i = 0; i < nparts; ++i) f += partial[i];
+  const int64_t total = (int64_t)n * n;
   const double sigma = shift_scale * sqrt(f) + 1e-30;
-  if (threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     ctl->sigma = sigma;
     ctl->sweeps_done = 0;
     ctl->stop_ratio2 = stop_ratio2;
+    ctl->f32_sweeps = 0;
+    ctl->f32_last_ratio2 = 0.f;
     for (int i = 0; i < 64; ++i) ctl->rotations[i] = 0;
     for (int i = 0; i < 48; ++i) ctl->max_ratio2[i] = 0u;
   }
-  for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
     int j = (int)(e / n), i = (int)(e % n);
     double2 v = A[(int64_t)i * n + j];            // G[i][j] = A'[i][j]; GT[j][i]
     // Hermitian input: use the average of A[i][j] and conj(A[j][i]) to be robust to tiny asymmetries
@@ -1188,6 +1199,7 @@ static int launch_jacobi_cluster(double2* GT, int n, int max_sweeps, double tol,
 // Hermitian eigendecomposition of A[n,n] (n a power of two >= 2): evals[n], VT (rows = eigenvectors).
 // ws: GT[n*n] double2, then JacobiCtl.
 #include "eig_mixed.cuh"
+#include "eig_line.cuh"
 
 // stop_ratio2: see JacobiCtl.  The eigenvalue problem is solved on A + sigma I (sigma = 2 ||A||_F), so a relative off-diagonal
 // |gamma| / sqrt(a b) = r between two columns whose eigenvalues differ by `gap` means an eigenvector mixing of r sigma / (2 gap):
@@ -1196,22 +1208,36 @@ static int launch_jacobi_cluster(double2* GT, int n, int max_sweeps, double tol,
 // N = 6 / 8 (benchmarks/jacobi_sweeps.py) the sweep after such a start leaves 1e-11 .. 8e-9 -- three orders below the 1e-5 bar on rho --
 // and it saves one of nine sweeps against the round-1 threshold of 1e-7.  (The sweep count itself is the cyclic method's: a slow, roughly
 // halving phase over sweeps 2-7 while the 250 clustered noise eigenvalues separate; a 40x smaller shift does not shorten it.)
-// extra / extra_bytes: optional scratch of 24 n^2 bytes; when present (and 64 <= n <= 256) the sweeps start in fp32 (eig_mixed.cuh).
+// extra / extra_bytes: optional scratch of 24 n^2 bytes; when present (and 64 <= n <= 1024) the sweeps start in fp32 (eig_mixed.cuh).
+// 256 < n <= 1024 runs on the multi-CTA line kernel (eig_line.cuh; mailboxes in the not-yet-written VT buffer), fp32 and fp64 alike.
 static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char* ws, cudaStream_t s, float stop_ratio2 = 1e-11f,
                        char* extra = nullptr, int64_t extra_bytes = 0) {
   double2* GT = (double2*)ws;
   JacobiCtl* ctl = (JacobiCtl*)(ws + (int64_t)16 * n * n);
   static double shift_scale = -1.0;
   if (shift_scale < 0.0) { const char* e = getenv("DDQST_JACOBI_SHIFT_SCALE"); shift_scale = e ? atof(e) : 2.0; }
-  jacobi_init_kernel<<<1, 1024, 0, s>>>(A, n, GT, ctl, stop_ratio2, shift_scale);
-  DDQST_LAUNCH_OK();
+  {
+    const int64_t total = (int64_t)n * n;
+    int parts = (int)((total + 255) / 256);
+    if (parts > num_sms()) parts = num_sms();
+    double* partial = (double*)VT;                       // the eigenvector buffer is written last: scratch until then
+    jacobi_norm_kernel<<<parts, 256, 0, s>>>(A, total, partial);
+    DDQST_LAUNCH_OK();
+    int fill = (int)((total + 1023) / 1024);
+    if (fill > 4 * num_sms()) fill = 4 * num_sms();
+    jacobi_init_kernel<<<fill, 256, 0, s>>>(A, n, GT, ctl, stop_ratio2, shift_scale, partial, parts);
+    DDQST_LAUNCH_OK();
+  }
   int max_sweeps = 60;
   double tol = 1e-15;
   bool ring_done = false;
   static int mixed_env = -1;
   if (mixed_env < 0) { const char* e = getenv("DDQST_JACOBI_MIXED"); mixed_env = (e && e[0] == '0') ? 0 : 1; }
   const int64_t nn = (int64_t)n * n;
-  if (mixed_env == 1 && extra && extra_bytes >= 24 * nn && n >= 64 && n <= 256) {
+  static int line_env = -1;
+  if (line_env < 0) { const char* e = getenv("DDQST_JACOBI_LINE"); line_env = (e && e[0] == '0') ? 0 : 1; }
+  const bool line_ok = line_env == 1 && (n == 512 || n == 1024);
+  if (mixed_env == 1 && extra && extra_bytes >= 24 * nn && n >= 64 && (n <= 256 || line_ok)) {
     double2* X1 = (double2*)extra;
     float2* G32 = (float2*)(extra + 16 * nn);
     eig_to_f32_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(GT, G32, nn);
@@ -1222,32 +1248,34 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
     {
       JacobiCtl* c32 = ctl;                     // same control block; its stop threshold is rewritten below for the fp64 phase
       // set the fp32 stop threshold (init wrote the fp64 one)
-      eig_set_stop_kernel<<<1, 32, 0, s>>>(c32, 1e-10f);
+      // (n > 256: an fp64 step of the line kernel costs 1.3 fp32 steps, so the hand-over comes a sweep or two earlier -- measured
+      // 7 + 3 sweeps instead of 9 + 2 at n = 1024)
+      static float f32_stop_env = -1.f;
+      if (f32_stop_env < 0.f) { const char* e = getenv("DDQST_JACOBI_F32_STOP"); f32_stop_env = e ? (float)atof(e) : 0.f; }
+      const float f32_stop = f32_stop_env > 0.f ? f32_stop_env : (n > 256 ? 1e-8f : 1e-10f);
+      eig_set_stop_kernel<<<1, 32, 0, s>>>(c32, f32_stop);
       DDQST_LAUNCH_OK();
       const int epl = n / 32;
-      switch (epl) {
+      if (n > 256) {
+        if (n == 512) DDQST_TRY((launch_jacobi_line<float, 8>(G32, n, 20, 1e-7f, c32, (uint8_t*)VT, 16 * nn, s, &f32_done)));
+        else DDQST_TRY((launch_jacobi_line<float, 16>(G32, n, 20, 1e-7f, c32, (uint8_t*)VT, 16 * nn, s, &f32_done)));
+      } else switch (epl) {
         case 2: DDQST_TRY(launch_jacobi_oddeven_f32<2>(G32, n, 20, 1e-7f, c32, s, &f32_done)); break;
         case 4: DDQST_TRY(launch_jacobi_oddeven_f32<4>(G32, n, 20, 1e-7f, c32, s, &f32_done)); break;
         default: DDQST_TRY(launch_jacobi_oddeven_f32<8>(G32, n, 20, 1e-7f, c32, s, &f32_done)); break;
       }
     }
     if (f32_done) {
-      dim3 grid((n + 15) / 16, (n + 15) / 16), blk(16, 16);
       eig_normalise_rows_kernel<<<n, 128, 0, s>>>(G32, n, VT, ctl, stop_ratio2);          // R (rows = eigenvector estimates), ctl reset
       DDQST_LAUNCH_OK();
       // two Newton-Schulz steps: the fp32 columns are orthogonal to ~1e-5 x sqrt(n), one step leaves ~1e-7 (measured: 2e-6 in the
       // eigenvalues), the second ~1e-14
-      eig_zgemm_kernel<0><<<grid, blk, 0, s>>>(VT, VT, nullptr, n, ctl, X1);               // M = R R^H
-      DDQST_LAUNCH_OK();
-      eig_zgemm_kernel<1><<<grid, blk, 0, s>>>(X1, VT, VT, n, ctl, GT);                    // R1 = 1.5 R - 0.5 M R   (into the GT buffer)
-      DDQST_LAUNCH_OK();
-      eig_zgemm_kernel<0><<<grid, blk, 0, s>>>(GT, GT, nullptr, n, ctl, X1);               // M1 = R1 R1^H
-      DDQST_LAUNCH_OK();
-      eig_zgemm_kernel<1><<<grid, blk, 0, s>>>(X1, GT, GT, n, ctl, VT);                    // R2 = 1.5 R1 - 0.5 M1 R1 (into the VT buffer)
-      DDQST_LAUNCH_OK();
+      DDQST_TRY(launch_eig_zgemm<0>(VT, VT, nullptr, n, ctl, X1, s));                      // M = R R^H
+      DDQST_TRY(launch_eig_zgemm<1>(X1, VT, VT, n, ctl, GT, s));                           // R1 = 1.5 R - 0.5 M R   (into the GT buffer)
+      DDQST_TRY(launch_eig_zgemm<0>(GT, GT, nullptr, n, ctl, X1, s));                      // M1 = R1 R1^H
+      DDQST_TRY(launch_eig_zgemm<1>(X1, GT, GT, n, ctl, VT, s));                           // R2 = 1.5 R1 - 0.5 M1 R1 (into the VT buffer)
       DDQST_CUDA_OK(cudaMemcpyAsync(GT, VT, 16 * nn, cudaMemcpyDeviceToDevice, s));
-      eig_zgemm_kernel<2><<<grid, blk, 0, s>>>(GT, A, nullptr, n, ctl, X1);                // G = A' R'^T as rows: X1[j][:] = A' v_j
-      DDQST_LAUNCH_OK();
+      DDQST_TRY(launch_eig_zgemm<2>(GT, A, nullptr, n, ctl, X1, s));                       // G = A' R'^T as rows: X1[j][:] = A' v_j
       GT = X1;                                                                            // the fp64 sweeps and the read-out work on X1
     }
   }
@@ -1287,6 +1315,12 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
       default: DDQST_TRY(launch_jacobi_cluster<8>(GT, n, max_sweeps, tol, ctl, csize, s)); break;
     }
   } else {
+    if (line_ok) {                                     // the eigenvector buffer is written only after the sweeps: it hosts the mailboxes
+      if (n == 512) DDQST_TRY((launch_jacobi_line<double, 8>(GT, n, max_sweeps, tol, ctl, (uint8_t*)VT, 16 * nn, s, &ring_done)));
+      else DDQST_TRY((launch_jacobi_line<double, 16>(GT, n, max_sweeps, tol, ctl, (uint8_t*)VT, 16 * nn, s, &ring_done)));
+    }
+  }
+  if (!ring_done && n > 256) {
     int per_sm = 0;
     DDQST_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_sweeps_kernel, 256, 0));
     int grid = n / 2;
@@ -1310,6 +1344,15 @@ static int launch_rayleigh(const double2* M, const double2* VT, int n, double* e
 }
 
 int recon_tc_abort_fetch() { return tc_abort_fetch(); }
+#ifdef DDQST_JL_PROFILE
+extern "C" int ddqst_debug_jl_profile(long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_jl_prof, sizeof(long long) * 32);
+  long long z[32] = {0};
+  cudaMemcpyToSymbol(g_jl_prof, z, sizeof(z));
+  return 0;
+}
+#endif
 #ifdef DDQST_JR_PROFILE
 extern "C" int ddqst_debug_jr_profile(long long* out) {
   cudaDeviceSynchronize();

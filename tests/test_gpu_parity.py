@@ -704,3 +704,22 @@ def test_recon_report_mixed_target_against_oracle(dq, N):
     assert np.allclose(dq.get_metrics(rho, N), rep.metrics(), atol=1e-7)
     pure = dq.recon_report(h, N, psi)
     assert abs(pure.fidelity - orc.state_fidelity(psi, want_rho)) < 1e-5
+
+
+@pytest.mark.parametrize("dim", [512, 1024])
+def test_large_eigensolver_line_kernel(dq, dim):
+    """N = 9 / 10: the multi-CTA line kernel (csrc/eig_line.cuh; fp32 sweeps, Newton-Schulz, fp64 finish) against LAPACK on a
+    tomography-like matrix (rank-one signal + white Hermitian noise): PSD projection (RQC/reconstruct.py:48-54) to 1e-9 -- the bar
+    is 1e-5 --, idempotence, and the mixed-state fidelity (RQC/evaluate.py:70-97) between two such projections to 1e-6."""
+    from benchmarks.eig_large import tomography_like, psd_numpy, fidelity_numpy
+    _, rho = tomography_like(dim, 11)
+    _, rho2 = tomography_like(dim, 12)
+    want, want2 = psd_numpy(rho), psd_numpy(rho2)
+    got = dq.make_positive_semidefinite(dq.DensityMatrix(torch.from_numpy(rho).cuda()))
+    assert np.abs(got.data - want).max() < 1e-9
+    assert abs(np.trace(got.data).real - 1) < 1e-9
+    again = dq.make_positive_semidefinite(got)
+    assert np.abs(again.data - got.data).max() < 1e-9
+    got2 = dq.make_positive_semidefinite(dq.DensityMatrix(torch.from_numpy(rho2).cuda()))
+    assert abs(dq.state_fidelity(got, got2) - fidelity_numpy(want, want2)) < 1e-6
+    assert dq._lib.load().ddqst_debug_tc_status() == 0
