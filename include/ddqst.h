@@ -150,7 +150,7 @@ int ddqst_linear_inversion(const uint32_t* hist, const int64_t* shots, int32_t n
 /* ---- R4: make_positive_semidefinite (RQC/reconstruct.py:48-54): Hermitian eigendecomposition
  * (parallel cyclic Jacobi, fp64), clip, renormalise, rebuild; in place on rho[dim,dim] complex128.
  * evals_out (nullable) [dim] receives the clipped, renormalised spectrum.
- * workspace: 2 * 16 * dim^2 + 8 * dim + 1024 bytes; with 24 * dim^2 bytes more (64 <= dim <= 256) the Jacobi sweeps start in fp32
+ * workspace: 2 * 16 * dim^2 + 8 * dim + 1024 bytes; with 24 * dim^2 bytes more (64 <= dim <= 1024) the Jacobi sweeps start in fp32
  * and only the last 2-3 run in fp64 (same result, ~35 % less time). */
 int ddqst_psd_project(double* rho, int32_t dim, double* evals_out, void* workspace, int64_t ws_bytes, void* stream);
 
