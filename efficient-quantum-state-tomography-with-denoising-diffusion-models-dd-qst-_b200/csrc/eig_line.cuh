@@ -195,7 +195,7 @@ template <typename R> __device__ __forceinline__ R jl_reduce4(R v0, R v1, R v2, 
 // Rotation, first half: the outgoing column, straight to its destination (DST 0: shared-memory inbox / park slot, DST 1: mailbox).
 //   ODD  step (lower = P, upper = Q):  Q <- Q p;  out = c P - s Q   (rotated lower -> upper position -> right neighbour)
 //   EVEN step (lower = Q, upper = P):  P <- P p;  out = s Q + c P   (rotated upper -> lower position -> left neighbour)
-template <bool ODD, int DST, typename V, typename R, int EPL>
+template <bool ODD, int DST, bool SWAP, typename V, typename R, int EPL>
 __device__ __forceinline__ void jl_rotate_out(V (&P)[EPL], V (&Q)[EPL], R c, R s, R pr, R pi, uint8_t* dst, int t, uint32_t gen) {
 #pragma unroll
   for (int e = 0; e < EPL; ++e) {
@@ -204,7 +204,10 @@ __device__ __forceinline__ void jl_rotate_out(V (&P)[EPL], V (&Q)[EPL], R c, R s
   }
   auto out = [&](int e, int im) -> R {
     const R p = im ? P[e].y : P[e].x, q = im ? Q[e].y : Q[e].x;
-    return ODD ? c * p - s * q : s * q + c * p;
+    // with (p, q) the pair after the phase multiply: rotated lower / upper column =  ODD: c p - s q / s p + c q,  EVEN: c q - s p / c p + s q.
+    // SWAP (the columns exchange positions after the rotation, the hand-over rule of the line ordering): the rotated lower (ODD) or
+    // upper (EVEN) column leaves; without SWAP the rotated version of Q itself moves on.
+    return ODD ? (SWAP ? c * p - s * q : s * p + c * q) : (SWAP ? c * p + s * q : c * q - s * p);
   };
   if (DST == 0) {
     constexpr int PER = JlChunk<V>::PER;
@@ -238,14 +241,19 @@ __device__ __forceinline__ void jl_rotate_out(V (&P)[EPL], V (&Q)[EPL], R c, R s
   }
 }
 // second half: the staying column, in place in P, and its norm for the next step
-template <bool ODD, typename V, typename R, int EPL>
+template <bool ODD, bool SWAP, typename V, typename R, int EPL>
 __device__ __forceinline__ R jl_rotate_stay(V (&P)[EPL], const V (&Q)[EPL], R c, R s) {
   R n0 = 0, n1 = 0;
 #pragma unroll
   for (int e = 0; e < EPL; ++e) {
     V p;
-    if (ODD) { p.x = s * P[e].x + c * Q[e].x; p.y = s * P[e].y + c * Q[e].y; }        // rotated upper -> lower position: stays
-    else { p.x = c * Q[e].x - s * P[e].x; p.y = c * Q[e].y - s * P[e].y; }            // rotated lower -> upper position: stays
+    // the complement of jl_rotate_out; (P, Q) are the phase-multiplied pair it left behind
+    const V a = P[e], b = Q[e];
+    if (ODD) {
+      if (SWAP) { p.x = s * a.x + c * b.x; p.y = s * a.y + c * b.y; } else { p.x = c * a.x - s * b.x; p.y = c * a.y - s * b.y; }
+    } else {
+      if (SWAP) { p.x = c * b.x - s * a.x; p.y = c * b.y - s * a.y; } else { p.x = c * a.x + s * b.x; p.y = c * a.y + s * b.y; }
+    }
     P[e] = p;
     if (e & 1) n1 += p.x * p.x + p.y * p.y; else n0 += p.x * p.x + p.y * p.y;
   }
@@ -333,22 +341,22 @@ __global__ void __launch_bounds__(kJlThreads, 1) jacobi_line_kernel(typename JlV
         JL_STAMP(2);
         if (odd) {
           if (odd_to_mail) {
-            jl_rotate_out<true, 1, V, R, EPL>(P, Q, cc, ss, pr, pi, out_odd, t, g + 1u);
+            jl_rotate_out<true, 1, true, V, R, EPL>(P, Q, cc, ss, pr, pi, out_odd, t, g + 1u);
           } else {
-            jl_rotate_out<true, 0, V, R, EPL>(P, Q, cc, ss, pr, pi, out_odd, t, 0u);
+            jl_rotate_out<true, 0, true, V, R, EPL>(P, Q, cc, ss, pr, pi, out_odd, t, 0u);
             mbar_arrive(bar(grp + 1, 0));
           }
           JL_STAMP(3);
-          carry = jl_rotate_stay<true, V, R, EPL>(P, Q, cc, ss);
+          carry = jl_rotate_stay<true, true, V, R, EPL>(P, Q, cc, ss);
         } else {
           if (even_to_mail) {
-            jl_rotate_out<false, 1, V, R, EPL>(P, Q, cc, ss, pr, pi, out_even, t, g + 1u);
+            jl_rotate_out<false, 1, true, V, R, EPL>(P, Q, cc, ss, pr, pi, out_even, t, g + 1u);
           } else {
-            jl_rotate_out<false, 0, V, R, EPL>(P, Q, cc, ss, pr, pi, out_even, t, 0u);
+            jl_rotate_out<false, 0, true, V, R, EPL>(P, Q, cc, ss, pr, pi, out_even, t, 0u);
             if (!first) mbar_arrive(bar(grp - 1, 1));
           }
           JL_STAMP(3);
-          carry = jl_rotate_stay<false, V, R, EPL>(P, Q, cc, ss);
+          carry = jl_rotate_stay<false, true, V, R, EPL>(P, Q, cc, ss);
         }
         JL_STAMP(4);
       }
@@ -440,6 +448,190 @@ static int launch_jacobi_line(typename JlVec<R>::V* GT, int n, int max_sweeps, R
   return DDQST_OK;
 }
 
+// ================================================================================================ two-level (block) ordering
+// The line kernel pays one L2 hand-over (~1 900 cycles) on the critical path of EVERY step.  Here the line is made of BLOCKS of four
+// columns: a CTA owns two adjacent blocks -- group i keeps one column of each, P_i and Q -- and a block step rotates all 16 cross
+// pairs in four local steps (the Q columns go round the four groups through shared memory, one __syncthreads per local step);
+// only the fourth local step applies the line rule -- swap, lower block to the left neighbour CTA after even block steps, upper block
+// to the right after odd ones -- through the mailboxes, so three steps in four never leave the SM.  n/4 block steps bring every pair
+// of blocks together once; pairs inside a block are rotated once per sweep, at its start, out of shared memory.
+template <typename V, typename R, int EPL>
+__device__ __forceinline__ bool jl_pair_angle(const V (&P)[EPL], const V (&Q)[EPL], R carry, bool odd, R* rp, int lane, int wig, int grp,
+                                              R tol, R& cc, R& ss, R& pr, R& pi, float& worst) {
+  R q0 = 0, q1 = 0, r0 = 0, r1 = 0, i0 = 0, i1 = 0;                      // |Q|^2 and d = conj(P) . Q, two accumulators each
+#pragma unroll
+  for (int e = 0; e < EPL; e += 2) {
+    q0 += Q[e].x * Q[e].x + Q[e].y * Q[e].y;
+    r0 += P[e].x * Q[e].x + P[e].y * Q[e].y;
+    i0 += P[e].x * Q[e].y - P[e].y * Q[e].x;
+    q1 += Q[e + 1].x * Q[e + 1].x + Q[e + 1].y * Q[e + 1].y;
+    r1 += P[e + 1].x * Q[e + 1].x + P[e + 1].y * Q[e + 1].y;
+    i1 += P[e + 1].x * Q[e + 1].y - P[e + 1].y * Q[e + 1].x;
+  }
+  const R tot = jl_reduce4<R>(carry, q0 + q1, r0 + r1, i0 + i1, lane);
+  if ((lane & 7) == 0) rp[wig * 4 + (lane >> 3)] = tot;
+  jl_bar_sync(1 + grp, 64);
+  const R np = rp[0] + rp[4], nq = rp[1] + rp[5], dr = rp[2] + rp[6], di = rp[3] + rp[7];
+  const R sa = odd ? np : nq, sb = odd ? nq : np, gr = dr, gi = odd ? di : -di;
+  worst = fmaxf(worst, (float)((gr * gr + gi * gi) / (sa * sb)));
+  cc = 1; ss = 0; pr = 1; pi = 0;
+  return jl_angle(sa, sb, gr, gi, tol, cc, ss, pr, pi);
+}
+
+template <typename R, int EPL>
+__global__ void __launch_bounds__(kJlThreads, 1) jacobi_block_kernel(typename JlVec<R>::V* __restrict__ GT, int n, int max_sweeps, R tol,
+                                                                     JacobiCtl* ctl, uint8_t* __restrict__ comm0, uint8_t* __restrict__ comm1) {
+  typedef typename JlVec<R>::V V;
+  extern __shared__ __align__(16) uint8_t jl_smem[];
+  constexpr int COLB = EPL * 64 * (int)sizeof(V);
+  constexpr int MAILB = JlMail<V, EPL>::BYTES;
+  const int tid = threadIdx.x, grp = tid >> 6, t = tid & 63, lane = tid & 31, wig = (tid >> 5) & 1;
+  const int c = blockIdx.x, nc = gridDim.x;
+  const bool first = c == 0, last = c == nc - 1;
+  // shared memory: 8 column slots (local inboxes [group][parity]; the within-block phase keeps the CTA's 8 columns there), 4 park slots
+  // (CTA 0 parks its lower block during odd block steps), reduction scratch [group][parity][warp][4]
+  auto slot = [&](int i) { return jl_smem + i * COLB; };
+  R* red = reinterpret_cast<R*>(jl_smem + 12 * COLB) + grp * 16;
+  unsigned int* gbar = reinterpret_cast<unsigned int*>(comm0);
+  // mailbox [direction][CTA][group]: direction 0 = filled by the left neighbour (after odd block steps), 1 = by the right one
+  auto mail = [&](int dir, int cta) { return (dir ? comm1 : comm0) + kJlHeader + (size_t)(cta * kJlGroups + grp) * MAILB; };
+
+  V P[EPL], Q[EPL];                                     // block step 0 is even: lower block = the Q columns, upper block = the P columns
+  jl_get<V, EPL>(reinterpret_cast<const uint8_t*>(GT + (int64_t)(8 * c + grp) * n), t, Q);
+  jl_get<V, EPL>(reinterpret_cast<const uint8_t*>(GT + (int64_t)(8 * c + 4 + grp) * n), t, P);
+  R carry = 0;
+  uint32_t rc = 0;                                      // reduction-scratch parity
+  int sweep = 0;
+  uint32_t gb = 0;                                      // block steps so far (mailbox generation)
+  const int nblk = n / 4;
+  for (; sweep < max_sweeps; ++sweep) {
+    int rot = 0;
+    float worst = 0.f;
+    // ---- pairs inside the two resident blocks: three rounds of (0,1)(2,3) / (0,2)(1,3) / (0,3)(1,2) out of shared memory
+    jl_put<V, EPL>(slot(grp), t, Q);
+    jl_put<V, EPL>(slot(4 + grp), t, P);
+    __syncthreads();
+#pragma unroll 1
+    for (int r = 0; r < 3; ++r) {
+      const int blk = grp >> 1, pi_ = grp & 1;
+      const int i = r == 0 ? 2 * pi_ : pi_, j = r == 0 ? 2 * pi_ + 1 : r == 1 ? pi_ + 2 : 3 - pi_;
+      jl_get<V, EPL>(slot(blk * 4 + i), t, P);
+      jl_get<V, EPL>(slot(blk * 4 + j), t, Q);
+      R np = 0;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) np += P[e].x * P[e].x + P[e].y * P[e].y;
+      R cc, ss, pr, pi;
+      if (jl_pair_angle<V, R, EPL>(P, Q, np, true, red + (rc++ & 1u) * 8, lane, wig, grp, tol, cc, ss, pr, pi, worst)) ++rot;
+      jl_rotate_out<true, 0, false, V, R, EPL>(P, Q, cc, ss, pr, pi, slot(blk * 4 + j), t, 0u);
+      (void)jl_rotate_stay<true, false, V, R, EPL>(P, Q, cc, ss);
+      jl_put<V, EPL>(slot(blk * 4 + i), t, P);
+      __syncthreads();
+    }
+    jl_get<V, EPL>(slot(grp), t, Q);
+    jl_get<V, EPL>(slot(4 + grp), t, P);
+    carry = 0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) carry += P[e].x * P[e].x + P[e].y * P[e].y;
+    __syncthreads();                                    // the slots turn back into inboxes
+    // ---- block steps
+    uint32_t lp = 0;                                    // local inbox parity
+#pragma unroll 1
+    for (int bs = 0; bs < nblk; ++bs, ++gb) {
+      const bool odd = (gb & 1u) != 0u;
+      if (!(odd && last)) {                             // in odd block steps the last CTA only holds the idle top block
+#pragma unroll 1
+        for (int ls = 0; ls < 4; ++ls) {
+          R cc, ss, pr, pi;
+          if (jl_pair_angle<V, R, EPL>(P, Q, carry, odd, red + (rc++ & 1u) * 8, lane, wig, grp, tol, cc, ss, pr, pi, worst)) ++rot;
+          if (ls < 3) {
+            uint8_t* dst = slot(((grp + 3) & 3) * 2 + (int)lp);      // the rotated Q moves on to group i-1
+            if (odd) { jl_rotate_out<true, 0, false, V, R, EPL>(P, Q, cc, ss, pr, pi, dst, t, 0u); carry = jl_rotate_stay<true, false, V, R, EPL>(P, Q, cc, ss); }
+            else { jl_rotate_out<false, 0, false, V, R, EPL>(P, Q, cc, ss, pr, pi, dst, t, 0u); carry = jl_rotate_stay<false, false, V, R, EPL>(P, Q, cc, ss); }
+            __syncthreads();
+            jl_get<V, EPL>(slot(grp * 2 + (int)lp), t, Q);
+            lp ^= 1u;
+          } else if (odd) {                             // upper block -> right neighbour
+            jl_rotate_out<true, 1, true, V, R, EPL>(P, Q, cc, ss, pr, pi, mail(0, c + 1), t, gb + 1u);
+            carry = jl_rotate_stay<true, true, V, R, EPL>(P, Q, cc, ss);
+          } else {                                      // lower block -> left neighbour (CTA 0 parks it)
+            if (first) jl_rotate_out<false, 0, true, V, R, EPL>(P, Q, cc, ss, pr, pi, slot(8 + grp), t, 0u);
+            else jl_rotate_out<false, 1, true, V, R, EPL>(P, Q, cc, ss, pr, pi, mail(1, c - 1), t, gb + 1u);
+            carry = jl_rotate_stay<false, true, V, R, EPL>(P, Q, cc, ss);
+          }
+        }
+      }
+      // the arriving block
+      if (!odd) {
+        if (!last) jl_collect<V, EPL>(mail(1, c), t, Q, gb + 1u, 71);
+      } else {
+        if (first) jl_get<V, EPL>(slot(8 + grp), t, Q);          // every thread reads back exactly the chunks it wrote
+        else jl_collect<V, EPL>(mail(0, c), t, Q, gb + 1u, 72);
+      }
+    }
+    if (t == 0) {
+      if (rot > 0) atomicAdd(&ctl->rotations[sweep], rot);
+      if (sweep < 48) atomicMax(&ctl->max_ratio2[sweep], __float_as_uint(worst));
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(gbar, 1u);
+      const unsigned int want = (unsigned int)(sweep + 1) * (unsigned int)nc;
+      long long start = 0;
+      uint32_t spins = 0;
+      while (jl_ld_acquire(gbar) < want) {
+        if ((++spins & 0xFFu) == 0) {
+          if (start == 0) start = clock64();
+          if (*((volatile int*)&g_tc_abort) != 0) break;
+          if (clock64() - start > 2000000000LL) { atomicCAS(&g_tc_abort, 0, 73); break; }
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    const int total = __ldcg(&ctl->rotations[sweep]);
+    if (total == 0) { ++sweep; break; }
+    if (sweep < 48 && __uint_as_float(__ldcg(&ctl->max_ratio2[sweep])) < __ldcg(&ctl->stop_ratio2)) { ++sweep; break; }
+    if (*((volatile int*)&g_tc_abort) != 0) { ++sweep; break; }
+  }
+  jl_put<V, EPL>(reinterpret_cast<uint8_t*>(GT + (int64_t)(8 * c + grp) * n), t, Q);
+  jl_put<V, EPL>(reinterpret_cast<uint8_t*>(GT + (int64_t)(8 * c + 4 + grp) * n), t, P);
+  if (c == 0 && tid == 0) ctl->sweeps_done = sweep;
+}
+
+template <typename R, int EPL>
+static int launch_jacobi_block(typename JlVec<R>::V* GT, int n, int max_sweeps, R tol, JacobiCtl* ctl, uint8_t* comm0, int64_t bytes0,
+                               uint8_t* comm1, int64_t bytes1, cudaStream_t s, bool* launched) {
+  typedef typename JlVec<R>::V V;
+  constexpr int COLB = EPL * 64 * (int)sizeof(V);
+  constexpr int smem = 12 * COLB + kJlGroups * 16 * (int)sizeof(R) + 16;
+  *launched = false;
+  if (n != EPL * 64 || n % 8 != 0) return DDQST_OK;
+  const int nc = n / 8;
+  const int64_t need = kJlHeader + (int64_t)nc * kJlGroups * JlMail<V, EPL>::BYTES;
+  if (comm0 == nullptr || comm1 == nullptr || bytes0 < need || bytes1 < need) return DDQST_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(jacobi_block_kernel<R, EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return DDQST_OK;
+    }
+    attr_set = true;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_block_kernel<R, EPL>, kJlThreads, smem) != cudaSuccess ||
+      (int64_t)per_sm * num_sms() < nc) {
+    (void)cudaGetLastError();
+    return DDQST_OK;
+  }
+  DDQST_CUDA_OK(cudaMemsetAsync(comm0, 0, (size_t)need, s));
+  DDQST_CUDA_OK(cudaMemsetAsync(comm1, 0, (size_t)need, s));
+  void* args[] = {&GT, &n, &max_sweeps, &tol, &ctl, &comm0, &comm1};
+  DDQST_CUDA_OK(cudaLaunchCooperativeKernel((void*)jacobi_block_kernel<R, EPL>, dim3((unsigned)nc), dim3(kJlThreads), args, smem, s));
+  *launched = true;
+  return DDQST_OK;
+}
+
 // ---- register-tiled fp64 complex GEMM for the glue at n >= 512 (64 x 64 tile per CTA, 4 x 4 outputs per thread); OP as eig_zgemm_kernel
 template <int OP>
 __global__ void __launch_bounds__(256) eig_zgemm64_kernel(const double2* __restrict__ A, const double2* __restrict__ B, const double2* __restrict__ A2,
@@ -457,9 +649,9 @@ __global__ void __launch_bounds__(256) eig_zgemm64_kernel(const double2* __restr
     for (int i = 0; i < 4; ++i) {                       // tiles read along k (row-major rows), stored k-major
       const int idx = tid + 256 * i, row = idx >> 4, kk = idx & 15;
       As[kk][row] = A[(int64_t)(r0 + row) * n + k0 + kk];
-      if (OP == 0) { const double2 v = B[(int64_t)(c0 + row) * n + k0 + kk]; Bs[kk][row] = make_double2(v.x, -v.y); }   // B^H
+      if (OP == 0 || OP == 4) { const double2 v = B[(int64_t)(c0 + row) * n + k0 + kk]; Bs[kk][row] = make_double2(v.x, OP == 0 ? -v.y : v.y); }   // B^H / B^T
     }
-    if (OP != 0) {
+    if (OP != 0 && OP != 4) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int idx = tid + 256 * i, kk = idx >> 6, cc = idx & 63;
@@ -498,7 +690,7 @@ __global__ void __launch_bounds__(256) eig_zgemm64_kernel(const double2* __restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int64_t e = (int64_t)(r0 + ty + 16 * i) * n + c0 + tx + 16 * j;
-      if (OP == 0) C[e] = make_double2(ax[i][j], ay[i][j]);
+      if (OP == 0 || OP == 4) C[e] = make_double2(ax[i][j], ay[i][j]);
       else if (OP == 1) { const double2 v = A2[e]; C[e] = make_double2(1.5 * v.x - 0.5 * ax[i][j], 1.5 * v.y - 0.5 * ay[i][j]); }
       else { const double2 v = A[e]; C[e] = make_double2(ax[i][j] + sg * v.x, ay[i][j] + sg * v.y); }
     }

@@ -234,6 +234,7 @@ __global__ void eig_normalise_rows_kernel(const float2* __restrict__ G32, int n,
 // OP 0: C = A . B^H            (M = R R^H)
 // OP 1: C = 1.5 A2 - 0.5 A . B (R' = 1.5 R - 0.5 M R ; A = M, B = R, A2 = R)
 // OP 2: C[j][i] = sum_k A[j][k] conj(H[k][i]) + sigma A[j][i]   (GT = R conj(A') with A' = H + sigma I; H Hermitian, symmetrised as in init)
+// OP 4: C = A . B^T            (no conjugate; the change of basis of the mixed-state fidelity)
 template <int OP>
 __global__ void eig_zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__ B, const double2* __restrict__ A2, int n,
                                  const JacobiCtl* ctl, double2* __restrict__ C) {
@@ -244,9 +245,9 @@ __global__ void eig_zgemm_kernel(const double2* __restrict__ A, const double2* _
     const int ka = k0 + threadIdx.x, kb = k0 + threadIdx.y;
     ta[threadIdx.y][threadIdx.x] = (r < n && ka < n) ? A[(int64_t)r * n + ka] : make_double2(0, 0);
     double2 bv = make_double2(0, 0);
-    if (OP == 0) {                                    // B^H[k][c] = conj(B[c][k]): read B[c0+ty... coalesced along k
+    if (OP == 0 || OP == 4) {                         // B^H[k][c] = conj(B[c][k]): read B[c0+ty... coalesced along k
       const int cc = blockIdx.x * 16 + threadIdx.y, kk = k0 + threadIdx.x;
-      if (cc < n && kk < n) { const double2 t = B[(int64_t)cc * n + kk]; bv = make_double2(t.x, -t.y); }
+      if (cc < n && kk < n) { const double2 t = B[(int64_t)cc * n + kk]; bv = make_double2(t.x, OP == 0 ? -t.y : t.y); }
       tb[threadIdx.x][threadIdx.y] = bv;              // tb[k][c]
     } else if (OP == 1) {
       if (kb < n && c < n) bv = B[(int64_t)kb * n + c];
@@ -270,8 +271,20 @@ __global__ void eig_zgemm_kernel(const double2* __restrict__ A, const double2* _
   }
   if (r < n && c < n) {
     const int64_t e = (int64_t)r * n + c;
-    if (OP == 0) C[e] = make_double2(ax, ay);
+    if (OP == 0 || OP == 4) C[e] = make_double2(ax, ay);
     else if (OP == 1) { const double2 v = A2[e]; C[e] = make_double2(1.5 * v.x - 0.5 * ax, 1.5 * v.y - 0.5 * ay); }
     else { const double2 v = A[e]; const double sg = ctl->sigma; C[e] = make_double2(ax + sg * v.x, ay + sg * v.y); }
+  }
+}
+
+// M[j][k] *= sqrt(max(l_j, 0) max(l_k, 0)): rows / columns of clipped eigenvalues become EXACT zeros (see fidelity_in_eigenbasis)
+__global__ void eig_scale_sqrt_kernel(double2* __restrict__ M, const double* __restrict__ ev, int n) {
+  const int64_t total = (int64_t)n * n;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(e / n), k = (int)(e % n);
+    const double lj = ev[j], lk = ev[k];
+    const double f = (lj > 0.0 && lk > 0.0) ? sqrt(lj * lk) : 0.0;
+    const double2 v = M[e];
+    M[e] = f > 0.0 ? make_double2(f * v.x, f * v.y) : make_double2(0.0, 0.0);
   }
 }

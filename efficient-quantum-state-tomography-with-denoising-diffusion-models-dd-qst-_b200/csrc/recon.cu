@@ -1209,7 +1209,8 @@ static int launch_jacobi_cluster(double2* GT, int n, int max_sweeps, double tol,
 // and it saves one of nine sweeps against the round-1 threshold of 1e-7.  (The sweep count itself is the cyclic method's: a slow, roughly
 // halving phase over sweeps 2-7 while the 250 clustered noise eigenvalues separate; a 40x smaller shift does not shorten it.)
 // extra / extra_bytes: optional scratch of 24 n^2 bytes; when present (and 64 <= n <= 1024) the sweeps start in fp32 (eig_mixed.cuh).
-// 256 < n <= 1024 runs on the multi-CTA line kernel (eig_line.cuh; mailboxes in the not-yet-written VT buffer), fp32 and fp64 alike.
+// 256 < n <= 1024 runs on the multi-CTA kernels of eig_line.cuh, fp32 and fp64 alike: the two-level block ordering when the scratch is there
+// (its mailboxes take the not-yet-written VT buffer and, in the fp64 phase, the first G buffer), else the line ordering (VT alone).
 static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char* ws, cudaStream_t s, float stop_ratio2 = 1e-11f,
                        char* extra = nullptr, int64_t extra_bytes = 0) {
   double2* GT = (double2*)ws;
@@ -1235,8 +1236,9 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
   if (mixed_env < 0) { const char* e = getenv("DDQST_JACOBI_MIXED"); mixed_env = (e && e[0] == '0') ? 0 : 1; }
   const int64_t nn = (int64_t)n * n;
   static int line_env = -1;
-  if (line_env < 0) { const char* e = getenv("DDQST_JACOBI_LINE"); line_env = (e && e[0] == '0') ? 0 : 1; }
-  const bool line_ok = line_env == 1 && (n == 512 || n == 1024);
+  if (line_env < 0) { const char* e = getenv("DDQST_JACOBI_LINE"); line_env = e ? atoi(e) : 2; }       // 0 cooperative kernel, 1 line ordering only, 2 block ordering where its scratch fits (default)
+  const bool line_ok = line_env >= 1 && (n == 512 || n == 1024);
+  const bool block_ok = line_env == 2;
   if (mixed_env == 1 && extra && extra_bytes >= 24 * nn && n >= 64 && (n <= 256 || line_ok)) {
     double2* X1 = (double2*)extra;
     float2* G32 = (float2*)(extra + 16 * nn);
@@ -1257,8 +1259,14 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
       DDQST_LAUNCH_OK();
       const int epl = n / 32;
       if (n > 256) {
-        if (n == 512) DDQST_TRY((launch_jacobi_line<float, 8>(G32, n, 20, 1e-7f, c32, (uint8_t*)VT, 16 * nn, s, &f32_done)));
-        else DDQST_TRY((launch_jacobi_line<float, 16>(G32, n, 20, 1e-7f, c32, (uint8_t*)VT, 16 * nn, s, &f32_done)));
+        if (block_ok) {
+          if (n == 512) DDQST_TRY((launch_jacobi_block<float, 8>(G32, n, 20, 1e-7f, c32, (uint8_t*)VT, 8 * nn, (uint8_t*)VT + 8 * nn, 8 * nn, s, &f32_done)));
+          else DDQST_TRY((launch_jacobi_block<float, 16>(G32, n, 20, 1e-7f, c32, (uint8_t*)VT, 8 * nn, (uint8_t*)VT + 8 * nn, 8 * nn, s, &f32_done)));
+        }
+        if (!f32_done) {
+          if (n == 512) DDQST_TRY((launch_jacobi_line<float, 8>(G32, n, 20, 1e-7f, c32, (uint8_t*)VT, 16 * nn, s, &f32_done)));
+          else DDQST_TRY((launch_jacobi_line<float, 16>(G32, n, 20, 1e-7f, c32, (uint8_t*)VT, 16 * nn, s, &f32_done)));
+        }
       } else switch (epl) {
         case 2: DDQST_TRY(launch_jacobi_oddeven_f32<2>(G32, n, 20, 1e-7f, c32, s, &f32_done)); break;
         case 4: DDQST_TRY(launch_jacobi_oddeven_f32<4>(G32, n, 20, 1e-7f, c32, s, &f32_done)); break;
@@ -1315,7 +1323,11 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
       default: DDQST_TRY(launch_jacobi_cluster<8>(GT, n, max_sweeps, tol, ctl, csize, s)); break;
     }
   } else {
-    if (line_ok) {                                     // the eigenvector buffer is written only after the sweeps: it hosts the mailboxes
+    if (line_ok && block_ok && GT != (double2*)ws) {   // mixed solve: the sweeps run on the scratch copy, the first G buffer is free as well
+      if (n == 512) DDQST_TRY((launch_jacobi_block<double, 8>(GT, n, max_sweeps, tol, ctl, (uint8_t*)VT, 16 * nn, (uint8_t*)ws, 16 * nn, s, &ring_done)));
+      else DDQST_TRY((launch_jacobi_block<double, 16>(GT, n, max_sweeps, tol, ctl, (uint8_t*)VT, 16 * nn, (uint8_t*)ws, 16 * nn, s, &ring_done)));
+    }
+    if (line_ok && !ring_done) {                       // the eigenvector buffer is written only after the sweeps: it hosts the mailboxes
       if (n == 512) DDQST_TRY((launch_jacobi_line<double, 8>(GT, n, max_sweeps, tol, ctl, (uint8_t*)VT, 16 * nn, s, &ring_done)));
       else DDQST_TRY((launch_jacobi_line<double, 16>(GT, n, max_sweeps, tol, ctl, (uint8_t*)VT, 16 * nn, s, &ring_done)));
     }
@@ -1341,6 +1353,32 @@ static int launch_rayleigh(const double2* M, const double2* VT, int n, double* e
   rayleigh_kernel<<<n, 256, smem, s>>>(M, VT, n, evals);
   DDQST_LAUNCH_OK();
   return DDQST_OK;
+}
+
+// Uhlmann fidelity spectrum in the eigenbasis of the first state.  With a = V diag(l) V^H,  sqrt(a) b sqrt(a)  is unitarily similar to
+// M' = diag(sqrt l) (V^H b V) diag(sqrt l), so F = (sum_i sqrt(lambda_i(M')))^2 from M' as well.  Two things are gained over forming
+// sqrt(a) b sqrt(a): (i) the rows / columns of clipped eigenvalues of a are EXACT zeros, so the zero cluster of the rank-deficient product
+// (half the spectrum after a PSD projection) is decoupled from the start -- the Jacobi rotations never touch those columns -- instead of
+// sitting in the matrix as rounding noise whose separation needed a relative off-diagonal of 1e-12 (the square roots amplify an
+// eigenvector mixing theta between 0 and lambda to sqrt(lambda) theta) and ten more fp64 sweeps with only linear convergence at
+// n = 1024; decoupled, the tail is quadratic again (3 fewer sweeps at the same final accuracy); (ii) no n^3 rebuild of sqrt(a).
+// The stop rule stays tight (a sweep that starts below 1e-10 is the last): the SECOND state may be rank deficient in a subspace that
+// is not aligned with this basis (measured: F off by 5e-6 at N = 8 with a full-rank a, a projected b and a 1e-7 rule; 3e-8 with 1e-9).
+// X: eigenvectors of a as rows (VT of jacobi_eigh), ev: its spectrum, b: the second state; T and M are n x n scratch, M receives conj(M').
+static int fidelity_in_eigenbasis(const double2* X, const double* ev, const double2* b, int n, double2* T, double2* M, cudaStream_t s) {
+  DDQST_TRY(launch_eig_zgemm<4>(X, b, nullptr, n, nullptr, T, s));            // T[j][q] = sum_p v_j[p] b[q][p]
+  DDQST_TRY(launch_eig_zgemm<0>(T, X, nullptr, n, nullptr, M, s));            // M[j][k] = sum_q T[j][q] conj(v_k[q]) = conj(v_j^H b v_k)
+  const int64_t total = (int64_t)n * n;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  eig_scale_sqrt_kernel<<<blocks, 256, 0, s>>>(M, ev, n);
+  DDQST_LAUNCH_OK();
+  return DDQST_OK;
+}
+static float fidelity_stop_ratio2() {
+  static float v = -1.f;
+  if (v < 0.f) { const char* e = getenv("DDQST_FIDELITY_STOP"); v = e ? (float)atof(e) : 1e-20f; }
+  return v;
 }
 
 int recon_tc_abort_fetch() { return tc_abort_fetch(); }
@@ -1507,15 +1545,17 @@ int ddqst_fidelity_mixed(const double* rho_a, const double* rho_b, int32_t dim, 
   double* evals = (double*)(jws + 16 * nn + 512);
   dim3 grid((dim + 15) / 16, (dim + 15) / 16), blk(16, 16);
   char* extra = ws_bytes >= need + 24 * nn ? ws + need : nullptr;              // optional: fp32 start of the sweeps (eig_mixed.cuh)
-  DDQST_TRY(jacobi_eigh((const double2*)rho_a, dim, evals, VT, jws, s, 1e-11f, extra, extra ? 24 * nn : 0));
-  rebuild_kernel<<<grid, blk, 0, s>>>(VT, evals, dim, 1, S);                    // sqrt(a), negatives clipped
-  DDQST_LAUNCH_OK();
-  zgemm_kernel<<<grid, blk, 0, s>>>(S, (const double2*)rho_b, dim, Tm);         // sqrt(a) b
-  DDQST_LAUNCH_OK();
-  zgemm_kernel<<<grid, blk, 0, s>>>(Tm, S, dim, VT);                            // M = sqrt(a) b sqrt(a) (reuse VT storage)
-  DDQST_LAUNCH_OK();
-  DDQST_CUDA_OK(cudaMemcpyAsync(Tm, VT, 16 * nn, cudaMemcpyDeviceToDevice, s));
-  DDQST_TRY(jacobi_eigh(Tm, dim, evals, VT, jws, s, 1e-24f, extra, extra ? 24 * nn : 0));
+  // the eigenvectors of a go into the change of basis: a null-space vector tilted by theta into the range of a gets the eigenvalue
+  // lambda theta^2 > 0 and survives the clipping with a square root of sqrt(lambda) theta.  The PSD projection's rule (a sweep that starts
+  // below 3.2e-6 is the last) left F off by 5e-6 at N = 6; already 1e-6 brings it to 2e-8, 3.2e-7 is used (one more fp64 sweep).
+  static float first_stop = -1.f;
+  if (first_stop < 0.f) { const char* e = getenv("DDQST_FIDELITY_FIRST_STOP"); first_stop = e ? (float)atof(e) : 1e-13f; }
+  DDQST_TRY(jacobi_eigh((const double2*)rho_a, dim, evals, VT, jws, s, first_stop, extra, extra ? 24 * nn : 0));
+  // eigenvalues of a as Rayleigh quotients: the solve works on a + sigma I, whose ~1e-13 absolute error would give each ZERO eigenvalue of a
+  // projected state a square root of 3e-7 (measured: F off by 5e-6 at N = 6)
+  DDQST_TRY(launch_rayleigh((const double2*)rho_a, VT, dim, evals, s));
+  DDQST_TRY(fidelity_in_eigenbasis(VT, evals, (const double2*)rho_b, dim, S, Tm, s));     // conj(M'), M' ~ sqrt(a) b sqrt(a)
+  DDQST_TRY(jacobi_eigh(Tm, dim, evals, VT, jws, s, fidelity_stop_ratio2(), extra, extra ? 24 * nn : 0));
   DDQST_TRY(launch_rayleigh(Tm, VT, dim, evals, s));
   sqrt_sum_sq_kernel<<<1, 256, 0, s>>>(evals, dim, out);
   DDQST_LAUNCH_OK();
@@ -1569,14 +1609,9 @@ int ddqst_recon_report(double* rho, int32_t num_qubits, const double* target, in
   } else if (target_kind == DDQST_TARGET_MIXED) {
     S = (double2*)(ws + 48 * nn + 16 * dim + 2048);
     double2* M = S + nn;
-    rebuild_kernel<<<grid, blk, 0, s>>>(VT, evals, dim, 1, S);                                  // sqrt(rho_psd) from the SAME eigenvectors
-    DDQST_LAUNCH_OK();
-    zgemm_kernel<<<grid, blk, 0, s>>>(S, (const double2*)target, dim, tmp);
-    DDQST_LAUNCH_OK();
-    zgemm_kernel<<<grid, blk, 0, s>>>(tmp, S, dim, M);
-    DDQST_LAUNCH_OK();
+    DDQST_TRY(fidelity_in_eigenbasis(VT, evals, (const double2*)target, dim, S, M, s));       // in the eigenbasis rho_psd already has
     char* extra2 = ws_bytes >= need + 24 * nn ? ws + need : nullptr;
-    DDQST_TRY(jacobi_eigh(M, dim, evals2, tmp, jws, s, 1e-24f, extra2, extra2 ? 24 * nn : 0));
+    DDQST_TRY(jacobi_eigh(M, dim, evals2, tmp, jws, s, fidelity_stop_ratio2(), extra2, extra2 ? 24 * nn : 0));
     DDQST_TRY(launch_rayleigh(M, tmp, dim, evals2, s));
     sqrt_sum_sq_kernel<<<1, 256, 0, s>>>(evals2, dim, report);
     DDQST_LAUNCH_OK();

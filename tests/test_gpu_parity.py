@@ -701,6 +701,7 @@ def test_recon_report_mixed_target_against_oracle(dq, N):
     # the separate entry points agree with the fused report
     rho = dq.linear_inversion(h, N)
     assert abs(dq.state_fidelity(dq.DensityMatrix(sigma), rho) - rep.fidelity) < 1e-7
+    assert abs(dq.state_fidelity(rho, dq.DensityMatrix(sigma)) - rep.fidelity) < 1e-7        # Uhlmann fidelity is symmetric
     assert np.allclose(dq.get_metrics(rho, N), rep.metrics(), atol=1e-7)
     pure = dq.recon_report(h, N, psi)
     assert abs(pure.fidelity - orc.state_fidelity(psi, want_rho)) < 1e-5
