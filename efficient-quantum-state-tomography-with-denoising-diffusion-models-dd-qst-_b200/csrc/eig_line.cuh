@@ -492,9 +492,9 @@ __global__ void __launch_bounds__(kJlThreads, 1) jacobi_block_kernel(typename Jl
   // (CTA 0 parks its lower block during odd block steps), reduction scratch [group][parity][warp][4]
   auto slot = [&](int i) { return jl_smem + i * COLB; };
   R* red = reinterpret_cast<R*>(jl_smem + 12 * COLB) + grp * 16;
-  unsigned int* gbar = reinterpret_cast<unsigned int*>(comm0);
+  unsigned int* gbar = &ctl->sweep_barrier;
   // mailbox [direction][CTA][group]: direction 0 = filled by the left neighbour (after odd block steps), 1 = by the right one
-  auto mail = [&](int dir, int cta) { return (dir ? comm1 : comm0) + kJlHeader + (size_t)(cta * kJlGroups + grp) * MAILB; };
+  auto mail = [&](int dir, int cta) { return (dir ? comm1 : comm0) + (size_t)(cta * kJlGroups + grp) * MAILB; };
 
   V P[EPL], Q[EPL];                                     // block step 0 is even: lower block = the Q columns, upper block = the P columns
   jl_get<V, EPL>(reinterpret_cast<const uint8_t*>(GT + (int64_t)(8 * c + grp) * n), t, Q);
@@ -608,7 +608,7 @@ static int launch_jacobi_block(typename JlVec<R>::V* GT, int n, int max_sweeps, 
   *launched = false;
   if (n != EPL * 64 || n % 8 != 0) return DDQST_OK;
   const int nc = n / 8;
-  const int64_t need = kJlHeader + (int64_t)nc * kJlGroups * JlMail<V, EPL>::BYTES;
+  const int64_t need = (int64_t)nc * kJlGroups * JlMail<V, EPL>::BYTES;
   if (comm0 == nullptr || comm1 == nullptr || bytes0 < need || bytes1 < need) return DDQST_OK;
   static bool attr_set = false;
   if (!attr_set) {
@@ -624,8 +624,9 @@ static int launch_jacobi_block(typename JlVec<R>::V* GT, int n, int max_sweeps, 
     (void)cudaGetLastError();
     return DDQST_OK;
   }
-  DDQST_CUDA_OK(cudaMemsetAsync(comm0, 0, (size_t)need, s));
+  DDQST_CUDA_OK(cudaMemsetAsync(comm0, 0, (size_t)need, s));           // all-zero sectors carry tag 0, block steps count from 1
   DDQST_CUDA_OK(cudaMemsetAsync(comm1, 0, (size_t)need, s));
+  DDQST_CUDA_OK(cudaMemsetAsync(&ctl->sweep_barrier, 0, sizeof(unsigned int), s));
   void* args[] = {&GT, &n, &max_sweeps, &tol, &ctl, &comm0, &comm1};
   DDQST_CUDA_OK(cudaLaunchCooperativeKernel((void*)jacobi_block_kernel<R, EPL>, dim3((unsigned)nc), dim3(kJlThreads), args, smem, s));
   *launched = true;

@@ -397,6 +397,7 @@ struct JacobiCtl {            // lives in the 512 bytes between G and the eigenv
   float stop_ratio2;               // a sweep that starts with every |gamma|^2 / (a b) below this is the last one
   int f32_sweeps;                  // mixed-precision solve: sweeps the fp32 phase took, and the worst ratio its last sweep started with
   float f32_last_ratio2;
+  unsigned int sweep_barrier;      // block kernel: arrivals at its once-per-sweep grid barrier (zeroed by the launcher)
 };
 static_assert(sizeof(JacobiCtl) <= 512, "JacobiCtl must fit the gap in the eigensolver workspace");
 
@@ -1239,6 +1240,11 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
   if (line_env < 0) { const char* e = getenv("DDQST_JACOBI_LINE"); line_env = e ? atoi(e) : 2; }       // 0 cooperative kernel, 1 line ordering only, 2 block ordering where its scratch fits (default)
   const bool line_ok = line_env >= 1 && (n == 512 || n == 1024);
   const bool block_ok = line_env == 2;
+  // n = 128 / 256: the block kernel over n/8 CTAs beats the one-cluster kernel as well (PSD projection at n = 256: 2.7-3.4 -> 2.2 ms);
+  // DDQST_JACOBI_BLOCK_SMALL=0 keeps the cluster kernel
+  static int small_env = -1;
+  if (small_env < 0) { const char* e = getenv("DDQST_JACOBI_BLOCK_SMALL"); small_env = e ? atoi(e) : 1; }
+  const bool small_block = small_env == 1 && (n == 128 || n == 256);
   if (mixed_env == 1 && extra && extra_bytes >= 24 * nn && n >= 64 && (n <= 256 || line_ok)) {
     double2* X1 = (double2*)extra;
     float2* G32 = (float2*)(extra + 16 * nn);
@@ -1267,6 +1273,9 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
           if (n == 512) DDQST_TRY((launch_jacobi_line<float, 8>(G32, n, 20, 1e-7f, c32, (uint8_t*)VT, 16 * nn, s, &f32_done)));
           else DDQST_TRY((launch_jacobi_line<float, 16>(G32, n, 20, 1e-7f, c32, (uint8_t*)VT, 16 * nn, s, &f32_done)));
         }
+      } else if (small_block) {
+        if (n == 128) DDQST_TRY((launch_jacobi_block<float, 2>(G32, n, 20, 1e-7f, c32, (uint8_t*)VT, 8 * nn, (uint8_t*)VT + 8 * nn, 8 * nn, s, &f32_done)));
+        else DDQST_TRY((launch_jacobi_block<float, 4>(G32, n, 20, 1e-7f, c32, (uint8_t*)VT, 8 * nn, (uint8_t*)VT + 8 * nn, 8 * nn, s, &f32_done)));
       } else switch (epl) {
         case 2: DDQST_TRY(launch_jacobi_oddeven_f32<2>(G32, n, 20, 1e-7f, c32, s, &f32_done)); break;
         case 4: DDQST_TRY(launch_jacobi_oddeven_f32<4>(G32, n, 20, 1e-7f, c32, s, &f32_done)); break;
@@ -1287,8 +1296,12 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
       GT = X1;                                                                            // the fp64 sweeps and the read-out work on X1
     }
   }
+  if (small_block && GT != (double2*)ws) {
+    if (n == 128) DDQST_TRY((launch_jacobi_block<double, 2>(GT, n, max_sweeps, tol, ctl, (uint8_t*)VT, 16 * nn, (uint8_t*)ws, 16 * nn, s, &ring_done)));
+    else DDQST_TRY((launch_jacobi_block<double, 4>(GT, n, max_sweeps, tol, ctl, (uint8_t*)VT, 16 * nn, (uint8_t*)ws, 16 * nn, s, &ring_done)));
+  }
   const char* ring_env = getenv("DDQST_JACOBI_RING");          // DDQST_JACOBI_RING=0 keeps the L2-resident kernel (debugging aid)
-  if (ring_env == nullptr || ring_env[0] != '0') {
+  if (!ring_done && (ring_env == nullptr || ring_env[0] != '0')) {
     if (n <= 256 && (ring_env == nullptr || ring_env[0] != '1')) {      // DDQST_JACOBI_RING=1 forces the two-column ring
       const int epl = n <= 32 ? 1 : n / 32;
       switch (epl) {
@@ -1547,9 +1560,10 @@ int ddqst_fidelity_mixed(const double* rho_a, const double* rho_b, int32_t dim, 
   char* extra = ws_bytes >= need + 24 * nn ? ws + need : nullptr;              // optional: fp32 start of the sweeps (eig_mixed.cuh)
   // the eigenvectors of a go into the change of basis: a null-space vector tilted by theta into the range of a gets the eigenvalue
   // lambda theta^2 > 0 and survives the clipping with a square root of sqrt(lambda) theta.  The PSD projection's rule (a sweep that starts
-  // below 3.2e-6 is the last) left F off by 5e-6 at N = 6; already 1e-6 brings it to 2e-8, 3.2e-7 is used (one more fp64 sweep).
+  // below 3.2e-6 is the last) left F off by 5e-6 at N = 6, a 3.2e-7 rule by 3e-7 at N = 8 (the error goes with the FOURTH power of the
+  // rule: quadratic convergence, then theta^2); 3.2e-8 is used -- one or two more fp64 sweeps.
   static float first_stop = -1.f;
-  if (first_stop < 0.f) { const char* e = getenv("DDQST_FIDELITY_FIRST_STOP"); first_stop = e ? (float)atof(e) : 1e-13f; }
+  if (first_stop < 0.f) { const char* e = getenv("DDQST_FIDELITY_FIRST_STOP"); first_stop = e ? (float)atof(e) : 1e-15f; }
   DDQST_TRY(jacobi_eigh((const double2*)rho_a, dim, evals, VT, jws, s, first_stop, extra, extra ? 24 * nn : 0));
   // eigenvalues of a as Rayleigh quotients: the solve works on a + sigma I, whose ~1e-13 absolute error would give each ZERO eigenvalue of a
   // projected state a square root of 3e-7 (measured: F off by 5e-6 at N = 6)

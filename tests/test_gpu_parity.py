@@ -707,20 +707,22 @@ def test_recon_report_mixed_target_against_oracle(dq, N):
     assert abs(pure.fidelity - orc.state_fidelity(psi, want_rho)) < 1e-5
 
 
-@pytest.mark.parametrize("dim", [512, 1024])
+@pytest.mark.parametrize("dim", [128, 256, 512, 1024])
 def test_large_eigensolver_line_kernel(dq, dim):
-    """N = 9 / 10: the multi-CTA line kernel (csrc/eig_line.cuh; fp32 sweeps, Newton-Schulz, fp64 finish) against LAPACK on a
-    tomography-like matrix (rank-one signal + white Hermitian noise): PSD projection (RQC/reconstruct.py:48-54) to 1e-9 -- the bar
+    """N = 7 .. 10: the multi-CTA block kernel (csrc/eig_line.cuh; fp32 sweeps, Newton-Schulz, fp64 finish) against LAPACK on a
+    tomography-like matrix (rank-one signal + white Hermitian noise): PSD projection (RQC/reconstruct.py:48-54) to 1e-7 -- the bar
     is 1e-5 --, idempotence, and the mixed-state fidelity (RQC/evaluate.py:70-97) between two such projections to 1e-6."""
     from benchmarks.eig_large import tomography_like, psd_numpy, fidelity_numpy
     _, rho = tomography_like(dim, 11)
     _, rho2 = tomography_like(dim, 12)
     want, want2 = psd_numpy(rho), psd_numpy(rho2)
     got = dq.make_positive_semidefinite(dq.DensityMatrix(torch.from_numpy(rho).cuda()))
-    assert np.abs(got.data - want).max() < 1e-9
+    assert np.abs(got.data - want).max() < 1e-7              # the stop rule leaves 1e-11 .. 1e-8 (DESIGN.md 5.4)
     assert abs(np.trace(got.data).real - 1) < 1e-9
     again = dq.make_positive_semidefinite(got)
-    assert np.abs(again.data - got.data).max() < 1e-9
+    # idempotent; the projected input is rank deficient, and eigenvectors of its smallest eigenvalues tilt into the null space by
+    # (final off-diagonal) x sigma / (2 lambda): 1e-7 here at n = 128, still two orders below the 1e-5 bar
+    assert np.abs(again.data - got.data).max() < 1e-6
     got2 = dq.make_positive_semidefinite(dq.DensityMatrix(torch.from_numpy(rho2).cuda()))
     assert abs(dq.state_fidelity(got, got2) - fidelity_numpy(want, want2)) < 1e-6
     assert dq._lib.load().ddqst_debug_tc_status() == 0
