@@ -478,8 +478,8 @@ __device__ __forceinline__ bool jl_pair_angle(const V (&P)[EPL], const V (&Q)[EP
   return jl_angle(sa, sb, gr, gi, tol, cc, ss, pr, pi);
 }
 
-template <typename R, int EPL>
-__global__ void __launch_bounds__(kJlThreads, 1) jacobi_block_kernel(typename JlVec<R>::V* __restrict__ GT, int n, int max_sweeps, R tol,
+template <typename R, int EPL, int G>
+__global__ void __launch_bounds__(64 * G, 1) jacobi_block_kernel(typename JlVec<R>::V* __restrict__ GT, int n, int max_sweeps, R tol,
                                                                      JacobiCtl* ctl, uint8_t* __restrict__ comm0, uint8_t* __restrict__ comm1) {
   typedef typename JlVec<R>::V V;
   extern __shared__ __align__(16) uint8_t jl_smem[];
@@ -488,47 +488,50 @@ __global__ void __launch_bounds__(kJlThreads, 1) jacobi_block_kernel(typename Jl
   const int tid = threadIdx.x, grp = tid >> 6, t = tid & 63, lane = tid & 31, wig = (tid >> 5) & 1;
   const int c = blockIdx.x, nc = gridDim.x;
   const bool first = c == 0, last = c == nc - 1;
-  // shared memory: 8 column slots (local inboxes [group][parity]; the within-block phase keeps the CTA's 8 columns there), 4 park slots
-  // (CTA 0 parks its lower block during odd block steps), reduction scratch [group][parity][warp][4]
+  // G columns per block (G groups of 64 threads per CTA; G = 4, or 8 for the latency-bound small n where a global hand-over every
+  // eighth step pays).  Shared memory: 2G column slots (local inboxes [group][parity]; the within-block phase keeps the CTA's 2G columns
+  // there), G park slots (CTA 0 parks its lower block during odd block steps), reduction scratch [group][parity][warp][4]
   auto slot = [&](int i) { return jl_smem + i * COLB; };
-  R* red = reinterpret_cast<R*>(jl_smem + 12 * COLB) + grp * 16;
+  R* red = reinterpret_cast<R*>(jl_smem + 3 * G * COLB) + grp * 16;
   unsigned int* gbar = &ctl->sweep_barrier;
   // mailbox [direction][CTA][group]: direction 0 = filled by the left neighbour (after odd block steps), 1 = by the right one
-  auto mail = [&](int dir, int cta) { return (dir ? comm1 : comm0) + (size_t)(cta * kJlGroups + grp) * MAILB; };
+  auto mail = [&](int dir, int cta) { return (dir ? comm1 : comm0) + (size_t)(cta * G + grp) * MAILB; };
 
   V P[EPL], Q[EPL];                                     // block step 0 is even: lower block = the Q columns, upper block = the P columns
-  jl_get<V, EPL>(reinterpret_cast<const uint8_t*>(GT + (int64_t)(8 * c + grp) * n), t, Q);
-  jl_get<V, EPL>(reinterpret_cast<const uint8_t*>(GT + (int64_t)(8 * c + 4 + grp) * n), t, P);
+  jl_get<V, EPL>(reinterpret_cast<const uint8_t*>(GT + (int64_t)(2 * G * c + grp) * n), t, Q);
+  jl_get<V, EPL>(reinterpret_cast<const uint8_t*>(GT + (int64_t)(2 * G * c + G + grp) * n), t, P);
   R carry = 0;
   uint32_t rc = 0;                                      // reduction-scratch parity
   int sweep = 0;
   uint32_t gb = 0;                                      // block steps so far (mailbox generation)
-  const int nblk = n / 4;
+  const int nblk = n / G;
   for (; sweep < max_sweeps; ++sweep) {
     int rot = 0;
     float worst = 0.f;
-    // ---- pairs inside the two resident blocks: three rounds of (0,1)(2,3) / (0,2)(1,3) / (0,3)(1,2) out of shared memory
+    // ---- pairs inside the two resident blocks: G-1 rounds of a round-robin tournament (circle method) out of shared memory,
+    //      block grp / (G/2), pair grp % (G/2)
     jl_put<V, EPL>(slot(grp), t, Q);
-    jl_put<V, EPL>(slot(4 + grp), t, P);
+    jl_put<V, EPL>(slot(G + grp), t, P);
     __syncthreads();
 #pragma unroll 1
-    for (int r = 0; r < 3; ++r) {
-      const int blk = grp >> 1, pi_ = grp & 1;
-      const int i = r == 0 ? 2 * pi_ : pi_, j = r == 0 ? 2 * pi_ + 1 : r == 1 ? pi_ + 2 : 3 - pi_;
-      jl_get<V, EPL>(slot(blk * 4 + i), t, P);
-      jl_get<V, EPL>(slot(blk * 4 + j), t, Q);
+    for (int r = 0; r < G - 1; ++r) {
+      const int blk = grp / (G / 2), k = grp % (G / 2);
+      int i = k == 0 ? G - 1 : (r + k) % (G - 1), j = k == 0 ? r : (r + (G - 1) - k) % (G - 1);
+      if (i > j) { const int tmp = i; i = j; j = tmp; }
+      jl_get<V, EPL>(slot(blk * G + i), t, P);
+      jl_get<V, EPL>(slot(blk * G + j), t, Q);
       R np = 0;
 #pragma unroll
       for (int e = 0; e < EPL; ++e) np += P[e].x * P[e].x + P[e].y * P[e].y;
       R cc, ss, pr, pi;
       if (jl_pair_angle<V, R, EPL>(P, Q, np, true, red + (rc++ & 1u) * 8, lane, wig, grp, tol, cc, ss, pr, pi, worst)) ++rot;
-      jl_rotate_out<true, 0, false, V, R, EPL>(P, Q, cc, ss, pr, pi, slot(blk * 4 + j), t, 0u);
+      jl_rotate_out<true, 0, false, V, R, EPL>(P, Q, cc, ss, pr, pi, slot(blk * G + j), t, 0u);
       (void)jl_rotate_stay<true, false, V, R, EPL>(P, Q, cc, ss);
-      jl_put<V, EPL>(slot(blk * 4 + i), t, P);
+      jl_put<V, EPL>(slot(blk * G + i), t, P);
       __syncthreads();
     }
     jl_get<V, EPL>(slot(grp), t, Q);
-    jl_get<V, EPL>(slot(4 + grp), t, P);
+    jl_get<V, EPL>(slot(G + grp), t, P);
     carry = 0;
 #pragma unroll
     for (int e = 0; e < EPL; ++e) carry += P[e].x * P[e].x + P[e].y * P[e].y;
@@ -540,11 +543,11 @@ __global__ void __launch_bounds__(kJlThreads, 1) jacobi_block_kernel(typename Jl
       const bool odd = (gb & 1u) != 0u;
       if (!(odd && last)) {                             // in odd block steps the last CTA only holds the idle top block
 #pragma unroll 1
-        for (int ls = 0; ls < 4; ++ls) {
+        for (int ls = 0; ls < G; ++ls) {
           R cc, ss, pr, pi;
           if (jl_pair_angle<V, R, EPL>(P, Q, carry, odd, red + (rc++ & 1u) * 8, lane, wig, grp, tol, cc, ss, pr, pi, worst)) ++rot;
-          if (ls < 3) {
-            uint8_t* dst = slot(((grp + 3) & 3) * 2 + (int)lp);      // the rotated Q moves on to group i-1
+          if (ls < G - 1) {
+            uint8_t* dst = slot(((grp + G - 1) % G) * 2 + (int)lp);  // the rotated Q moves on to group i-1
             if (odd) { jl_rotate_out<true, 0, false, V, R, EPL>(P, Q, cc, ss, pr, pi, dst, t, 0u); carry = jl_rotate_stay<true, false, V, R, EPL>(P, Q, cc, ss); }
             else { jl_rotate_out<false, 0, false, V, R, EPL>(P, Q, cc, ss, pr, pi, dst, t, 0u); carry = jl_rotate_stay<false, false, V, R, EPL>(P, Q, cc, ss); }
             __syncthreads();
@@ -554,7 +557,7 @@ __global__ void __launch_bounds__(kJlThreads, 1) jacobi_block_kernel(typename Jl
             jl_rotate_out<true, 1, true, V, R, EPL>(P, Q, cc, ss, pr, pi, mail(0, c + 1), t, gb + 1u);
             carry = jl_rotate_stay<true, true, V, R, EPL>(P, Q, cc, ss);
           } else {                                      // lower block -> left neighbour (CTA 0 parks it)
-            if (first) jl_rotate_out<false, 0, true, V, R, EPL>(P, Q, cc, ss, pr, pi, slot(8 + grp), t, 0u);
+            if (first) jl_rotate_out<false, 0, true, V, R, EPL>(P, Q, cc, ss, pr, pi, slot(2 * G + grp), t, 0u);
             else jl_rotate_out<false, 1, true, V, R, EPL>(P, Q, cc, ss, pr, pi, mail(1, c - 1), t, gb + 1u);
             carry = jl_rotate_stay<false, true, V, R, EPL>(P, Q, cc, ss);
           }
@@ -564,7 +567,7 @@ __global__ void __launch_bounds__(kJlThreads, 1) jacobi_block_kernel(typename Jl
       if (!odd) {
         if (!last) jl_collect<V, EPL>(mail(1, c), t, Q, gb + 1u, 71);
       } else {
-        if (first) jl_get<V, EPL>(slot(8 + grp), t, Q);          // every thread reads back exactly the chunks it wrote
+        if (first) jl_get<V, EPL>(slot(2 * G + grp), t, Q);          // every thread reads back exactly the chunks it wrote
         else jl_collect<V, EPL>(mail(0, c), t, Q, gb + 1u, 72);
       }
     }
@@ -594,32 +597,32 @@ __global__ void __launch_bounds__(kJlThreads, 1) jacobi_block_kernel(typename Jl
     if (sweep < 48 && __uint_as_float(__ldcg(&ctl->max_ratio2[sweep])) < __ldcg(&ctl->stop_ratio2)) { ++sweep; break; }
     if (*((volatile int*)&g_tc_abort) != 0) { ++sweep; break; }
   }
-  jl_put<V, EPL>(reinterpret_cast<uint8_t*>(GT + (int64_t)(8 * c + grp) * n), t, Q);
-  jl_put<V, EPL>(reinterpret_cast<uint8_t*>(GT + (int64_t)(8 * c + 4 + grp) * n), t, P);
+  jl_put<V, EPL>(reinterpret_cast<uint8_t*>(GT + (int64_t)(2 * G * c + grp) * n), t, Q);
+  jl_put<V, EPL>(reinterpret_cast<uint8_t*>(GT + (int64_t)(2 * G * c + G + grp) * n), t, P);
   if (c == 0 && tid == 0) ctl->sweeps_done = sweep;
 }
 
-template <typename R, int EPL>
+template <typename R, int EPL, int G = 4>
 static int launch_jacobi_block(typename JlVec<R>::V* GT, int n, int max_sweeps, R tol, JacobiCtl* ctl, uint8_t* comm0, int64_t bytes0,
                                uint8_t* comm1, int64_t bytes1, cudaStream_t s, bool* launched) {
   typedef typename JlVec<R>::V V;
   constexpr int COLB = EPL * 64 * (int)sizeof(V);
-  constexpr int smem = 12 * COLB + kJlGroups * 16 * (int)sizeof(R) + 16;
+  constexpr int smem = 3 * G * COLB + G * 16 * (int)sizeof(R) + 16;
   *launched = false;
-  if (n != EPL * 64 || n % 8 != 0) return DDQST_OK;
-  const int nc = n / 8;
-  const int64_t need = (int64_t)nc * kJlGroups * JlMail<V, EPL>::BYTES;
+  if (n != EPL * 64 || n % (2 * G) != 0 || n / (2 * G) < 2) return DDQST_OK;
+  const int nc = n / (2 * G);
+  const int64_t need = (int64_t)nc * G * JlMail<V, EPL>::BYTES;
   if (comm0 == nullptr || comm1 == nullptr || bytes0 < need || bytes1 < need) return DDQST_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(jacobi_block_kernel<R, EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(jacobi_block_kernel<R, EPL, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       (void)cudaGetLastError();
       return DDQST_OK;
     }
     attr_set = true;
   }
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_block_kernel<R, EPL>, kJlThreads, smem) != cudaSuccess ||
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_block_kernel<R, EPL, G>, 64 * G, smem) != cudaSuccess ||
       (int64_t)per_sm * num_sms() < nc) {
     (void)cudaGetLastError();
     return DDQST_OK;
@@ -628,7 +631,7 @@ static int launch_jacobi_block(typename JlVec<R>::V* GT, int n, int max_sweeps, 
   DDQST_CUDA_OK(cudaMemsetAsync(comm1, 0, (size_t)need, s));
   DDQST_CUDA_OK(cudaMemsetAsync(&ctl->sweep_barrier, 0, sizeof(unsigned int), s));
   void* args[] = {&GT, &n, &max_sweeps, &tol, &ctl, &comm0, &comm1};
-  DDQST_CUDA_OK(cudaLaunchCooperativeKernel((void*)jacobi_block_kernel<R, EPL>, dim3((unsigned)nc), dim3(kJlThreads), args, smem, s));
+  DDQST_CUDA_OK(cudaLaunchCooperativeKernel((void*)jacobi_block_kernel<R, EPL, G>, dim3((unsigned)nc), dim3(64 * G), args, smem, s));
   *launched = true;
   return DDQST_OK;
 }

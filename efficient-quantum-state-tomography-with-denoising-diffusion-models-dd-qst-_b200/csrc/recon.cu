@@ -1244,7 +1244,7 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
   // DDQST_JACOBI_BLOCK_SMALL=0 keeps the cluster kernel
   static int small_env = -1;
   if (small_env < 0) { const char* e = getenv("DDQST_JACOBI_BLOCK_SMALL"); small_env = e ? atoi(e) : 1; }
-  const bool small_block = small_env == 1 && (n == 128 || n == 256);
+  const bool small_block = small_env >= 1 && (n == 128 || n == 256);      // 1: blocks of 4 columns; 2: blocks of 8 (16 per CTA; measured 5-10 % slower)
   if (mixed_env == 1 && extra && extra_bytes >= 24 * nn && n >= 64 && (n <= 256 || line_ok)) {
     double2* X1 = (double2*)extra;
     float2* G32 = (float2*)(extra + 16 * nn);
@@ -1274,8 +1274,15 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
           else DDQST_TRY((launch_jacobi_line<float, 16>(G32, n, 20, 1e-7f, c32, (uint8_t*)VT, 16 * nn, s, &f32_done)));
         }
       } else if (small_block) {
-        if (n == 128) DDQST_TRY((launch_jacobi_block<float, 2>(G32, n, 20, 1e-7f, c32, (uint8_t*)VT, 8 * nn, (uint8_t*)VT + 8 * nn, 8 * nn, s, &f32_done)));
-        else DDQST_TRY((launch_jacobi_block<float, 4>(G32, n, 20, 1e-7f, c32, (uint8_t*)VT, 8 * nn, (uint8_t*)VT + 8 * nn, 8 * nn, s, &f32_done)));
+        uint8_t* c0 = (uint8_t*)VT;
+        uint8_t* c1 = c0 + 8 * nn;
+        if (small_env != 2) {
+          if (n == 128) DDQST_TRY((launch_jacobi_block<float, 2, 4>(G32, n, 20, 1e-7f, c32, c0, 8 * nn, c1, 8 * nn, s, &f32_done)));
+          else DDQST_TRY((launch_jacobi_block<float, 4, 4>(G32, n, 20, 1e-7f, c32, c0, 8 * nn, c1, 8 * nn, s, &f32_done)));
+        } else {
+          if (n == 128) DDQST_TRY((launch_jacobi_block<float, 2, 8>(G32, n, 20, 1e-7f, c32, c0, 8 * nn, c1, 8 * nn, s, &f32_done)));
+          else DDQST_TRY((launch_jacobi_block<float, 4, 8>(G32, n, 20, 1e-7f, c32, c0, 8 * nn, c1, 8 * nn, s, &f32_done)));
+        }
       } else switch (epl) {
         case 2: DDQST_TRY(launch_jacobi_oddeven_f32<2>(G32, n, 20, 1e-7f, c32, s, &f32_done)); break;
         case 4: DDQST_TRY(launch_jacobi_oddeven_f32<4>(G32, n, 20, 1e-7f, c32, s, &f32_done)); break;
@@ -1297,8 +1304,15 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
     }
   }
   if (small_block && GT != (double2*)ws) {
-    if (n == 128) DDQST_TRY((launch_jacobi_block<double, 2>(GT, n, max_sweeps, tol, ctl, (uint8_t*)VT, 16 * nn, (uint8_t*)ws, 16 * nn, s, &ring_done)));
-    else DDQST_TRY((launch_jacobi_block<double, 4>(GT, n, max_sweeps, tol, ctl, (uint8_t*)VT, 16 * nn, (uint8_t*)ws, 16 * nn, s, &ring_done)));
+    uint8_t* c0 = (uint8_t*)VT;
+    uint8_t* c1 = (uint8_t*)ws;
+    if (small_env != 2) {
+      if (n == 128) DDQST_TRY((launch_jacobi_block<double, 2, 4>(GT, n, max_sweeps, tol, ctl, c0, 16 * nn, c1, 16 * nn, s, &ring_done)));
+      else DDQST_TRY((launch_jacobi_block<double, 4, 4>(GT, n, max_sweeps, tol, ctl, c0, 16 * nn, c1, 16 * nn, s, &ring_done)));
+    } else {
+      if (n == 128) DDQST_TRY((launch_jacobi_block<double, 2, 8>(GT, n, max_sweeps, tol, ctl, c0, 16 * nn, c1, 16 * nn, s, &ring_done)));
+      else DDQST_TRY((launch_jacobi_block<double, 4, 8>(GT, n, max_sweeps, tol, ctl, c0, 16 * nn, c1, 16 * nn, s, &ring_done)));
+    }
   }
   const char* ring_env = getenv("DDQST_JACOBI_RING");          // DDQST_JACOBI_RING=0 keeps the L2-resident kernel (debugging aid)
   if (!ring_done && (ring_env == nullptr || ring_env[0] != '0')) {
