@@ -1566,11 +1566,10 @@ int ddqst_fidelity_mixed(const double* rho_a, const double* rho_b, int32_t dim, 
   cudaStream_t s = (cudaStream_t)stream;
   char* ws = (char*)workspace;
   double2* VT = (double2*)ws;
-  double2* S = (double2*)(ws + 16 * nn);       // sqrt(a)
-  double2* Tm = (double2*)(ws + 32 * nn);      // temp / M
+  double2* S = (double2*)(ws + 16 * nn);       // scratch of the change of basis
+  double2* Tm = (double2*)(ws + 32 * nn);      // M' (conjugated), see fidelity_in_eigenbasis
   char* jws = ws + 48 * nn;                    // GT (16nn) + ctl
   double* evals = (double*)(jws + 16 * nn + 512);
-  dim3 grid((dim + 15) / 16, (dim + 15) / 16), blk(16, 16);
   char* extra = ws_bytes >= need + 24 * nn ? ws + need : nullptr;              // optional: fp32 start of the sweeps (eig_mixed.cuh)
   // the eigenvectors of a go into the change of basis: a null-space vector tilted by theta into the range of a gets the eigenvalue
   // lambda theta^2 > 0 and survives the clipping with a square root of sqrt(lambda) theta.  The PSD projection's rule (a sweep that starts
