@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(256) histogram_kernel(const T* __restrict__ da
 // the same time; reading four counters before writing any adds compare instructions and becomes issue-bound).
 // Counters are folded into global memory with one atomicAdd per (warp, bin) at the end (and before a private
 // counter could overflow).
-template <typename T>
+// ATOMIC: the read-modify-write is ONE fire-and-forget shared-memory atomic on the lane's own 32-bit word (+1 or +65536 for the even /
+// odd bin of the pair) -- executed in the memory pipe, conflict free by the same layout, no load -> add -> store chain in the warp.
+template <typename T, bool ATOMIC>
 __global__ void __launch_bounds__(128) histogram_private_kernel(const T* __restrict__ data, int64_t n, int nbins,
                                                                 uint32_t* __restrict__ hist) {
   extern __shared__ __align__(16) uint8_t shp[];
@@ -97,8 +99,12 @@ __global__ void __launch_bounds__(128) histogram_private_kernel(const T* __restr
   const uint4* v4 = reinterpret_cast<const uint4*>(data);
   const uint32_t mask_bins = (uint32_t)nbins - 1u;
   auto bump = [&](uint32_t bin) {
-    uint16_t* c = reinterpret_cast<uint16_t*>(mine + ((bin >> 1) << 7) + ((bin & 1u) << 1));
-    *c = (uint16_t)(*c + 1);
+    if (ATOMIC) {
+      atomicAdd(reinterpret_cast<uint32_t*>(mine + ((bin >> 1) << 7)), 1u << ((bin & 1u) << 4));
+    } else {
+      uint16_t* c = reinterpret_cast<uint16_t*>(mine + ((bin >> 1) << 7) + ((bin & 1u) << 1));
+      *c = (uint16_t)(*c + 1);
+    }
   };
   auto fold = [&]() {                                   // warp-cooperative: lane l sums bins l, l+32, .. over all lanes
     __syncwarp();
@@ -162,6 +168,67 @@ __global__ void __launch_bounds__(128) histogram_private_kernel(const T* __restr
     for (int64_t i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) atomicAdd(hist + ((uint32_t)data[i] & mask_bins), 1u);
   __syncwarp();
   fold();
+}
+
+// N <= 8, second form: K interleaved 32-bit copies of the bins per warp, lane l adding into copy l % K with a fire-and-forget
+// shared-memory atomic (word = bin * K + copy).  One instruction per shot and no load -> add -> store chain to wait for, against
+// LDS / IADD / STS of the private-counter kernel; two lanes collide only when they share the copy AND their bins fall on the same bank.
+template <typename T, int K>
+__global__ void __launch_bounds__(256) histogram_copies_kernel(const T* __restrict__ data, int64_t n, int nbins, uint32_t* __restrict__ hist) {
+  extern __shared__ __align__(16) uint32_t hsh[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* w = hsh + (size_t)warp * nbins * K;
+  for (int i = lane; i < nbins * K; i += 32) w[i] = 0;
+  __syncwarp();
+  constexpr int VEC = 16 / sizeof(T);
+  const int64_t nvec = n / VEC;
+  const uint4* v4 = reinterpret_cast<const uint4*>(data);
+  const uint32_t mask_bins = (uint32_t)nbins - 1u;
+  uint32_t* mine = w + (lane & (K - 1));
+  auto load16 = [&](int64_t i) {
+    uint4 q;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(v4 + i));
+    return q;
+  };
+  auto consume = [&](const uint4& q) {
+    const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t x = words[k];
+      if (sizeof(T) == 1) {
+        atomicAdd(mine + ((x & mask_bins) * K), 1u); atomicAdd(mine + (((x >> 8) & mask_bins) * K), 1u);
+        atomicAdd(mine + (((x >> 16) & mask_bins) * K), 1u); atomicAdd(mine + (((x >> 24) & mask_bins) * K), 1u);
+      } else {
+        atomicAdd(mine + ((x & mask_bins) * K), 1u); atomicAdd(mine + (((x >> 16) & mask_bins) * K), 1u);
+      }
+    }
+  };
+  constexpr int DEPTH = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint4 buf[DEPTH];
+#pragma unroll
+  for (int d = 0; d < DEPTH; ++d) buf[d] = (i + d * stride < nvec) ? load16(i + d * stride) : make_uint4(0, 0, 0, 0);
+  for (; i < nvec; i += DEPTH * stride) {
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) {
+      const int64_t cur = i + d * stride;
+      if (cur >= nvec) break;
+      const uint4 q = buf[d];
+      const int64_t nxt = cur + DEPTH * stride;
+      if (nxt < nvec) buf[d] = load16(nxt);
+      consume(q);
+    }
+  }
+  if (blockIdx.x == 0)
+    for (int64_t j = nvec * VEC + threadIdx.x; j < n; j += blockDim.x) atomicAdd(hist + ((uint32_t)data[j] & mask_bins), 1u);
+  __syncwarp();
+  for (int bin = lane; bin < nbins; bin += 32) {
+    uint32_t sum = 0;
+#pragma unroll
+    for (int c = 0; c < K; ++c) sum += w[bin * K + ((c + lane) & (K - 1))];
+    if (sum) atomicAdd(hist + bin, sum);
+  }
 }
 
 // ------------------------------------------------------------------------------------ linear inversion
@@ -1443,16 +1510,55 @@ int ddqst_histogram(const void* packed, int elem_bytes, int64_t n, int32_t num_q
   DDQST_REQUIRE(((uintptr_t)packed & 15) == 0, DDQST_EINVAL_SHAPE, "packed bitstrings must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   const int nbins = 1 << num_qubits;
+  // DDQST_HIST_COPIES: 8 (default) = interleaved copies per warp + fire-and-forget shared atomics (8 copies up to 256 bins, 4 at 512,
+  // 2 at 1024: 8 KB per warp); 0 = private 16-bit counters; 1 = private counters bumped by one atomic; 2 / 4 / 16 = that many copies
+  static int copies_env = -1;
+  if (copies_env < 0) { const char* e = getenv("DDQST_HIST_COPIES"); copies_env = e ? atoi(e) : 8; }
+  if (num_qubits <= 10 && (copies_env == 2 || copies_env == 4 || copies_env == 8 || copies_env == 16)) {
+    const int64_t nv = n / (16 / elem_bytes);
+    int K = copies_env;
+    while (K > 2 && nbins * K > 2048) K >>= 1;
+    const int smem = 8 * nbins * K * 4;                  // 8 warps per CTA
+    const int per_sm = smem > 0 ? (220 * 1024) / smem : 1;
+    int64_t want_c = (nv + 255) / 256;
+    int64_t cap = (int64_t)num_sms() * (per_sm < 1 ? 1 : per_sm > 8 ? 8 : per_sm);
+    int grid_c = (int)(want_c < 1 ? 1 : want_c > cap ? cap : want_c);
+#define DDQST_HIST_COPIES_LAUNCH(TT, KK)                                                                                                  \
+    do {                                                                                                                                  \
+      DDQST_CUDA_OK(cudaFuncSetAttribute(histogram_copies_kernel<TT, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));            \
+      histogram_copies_kernel<TT, KK><<<grid_c, 256, smem, s>>>((const TT*)packed, n, nbins, hist);                                       \
+    } while (0)
+    if (elem_bytes == 1) {
+      if (K == 2) DDQST_HIST_COPIES_LAUNCH(uint8_t, 2); else if (K == 4) DDQST_HIST_COPIES_LAUNCH(uint8_t, 4);
+      else if (K == 8) DDQST_HIST_COPIES_LAUNCH(uint8_t, 8); else DDQST_HIST_COPIES_LAUNCH(uint8_t, 16);
+    } else {
+      if (K == 2) DDQST_HIST_COPIES_LAUNCH(uint16_t, 2); else if (K == 4) DDQST_HIST_COPIES_LAUNCH(uint16_t, 4);
+      else if (K == 8) DDQST_HIST_COPIES_LAUNCH(uint16_t, 8); else DDQST_HIST_COPIES_LAUNCH(uint16_t, 16);
+    }
+#undef DDQST_HIST_COPIES_LAUNCH
+    DDQST_LAUNCH_OK();
+    return DDQST_OK;
+  }
   if (num_qubits <= 8) {                                 // private 16-bit counters, no atomics in the streaming loop
     const int64_t nv = n / (16 / elem_bytes);
     int64_t want_p = (nv + 127) / 128;
     int grid_p = (int)(want_p < 1 ? 1 : (want_p > (int64_t)num_sms() * 3 ? (int64_t)num_sms() * 3 : want_p));
     if (elem_bytes == 1) {
-      DDQST_CUDA_OK(cudaFuncSetAttribute(histogram_private_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-      histogram_private_kernel<uint8_t><<<grid_p, 128, 65536, s>>>((const uint8_t*)packed, n, nbins, hist);
+      if (copies_env == 1) {
+        DDQST_CUDA_OK(cudaFuncSetAttribute(histogram_private_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        histogram_private_kernel<uint8_t, true><<<grid_p, 128, 65536, s>>>((const uint8_t*)packed, n, nbins, hist);
+      } else {
+        DDQST_CUDA_OK(cudaFuncSetAttribute(histogram_private_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        histogram_private_kernel<uint8_t, false><<<grid_p, 128, 65536, s>>>((const uint8_t*)packed, n, nbins, hist);
+      }
     } else {
-      DDQST_CUDA_OK(cudaFuncSetAttribute(histogram_private_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-      histogram_private_kernel<uint16_t><<<grid_p, 128, 65536, s>>>((const uint16_t*)packed, n, nbins, hist);
+      if (copies_env == 1) {
+        DDQST_CUDA_OK(cudaFuncSetAttribute(histogram_private_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        histogram_private_kernel<uint16_t, true><<<grid_p, 128, 65536, s>>>((const uint16_t*)packed, n, nbins, hist);
+      } else {
+        DDQST_CUDA_OK(cudaFuncSetAttribute(histogram_private_kernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        histogram_private_kernel<uint16_t, false><<<grid_p, 128, 65536, s>>>((const uint16_t*)packed, n, nbins, hist);
+      }
     }
     DDQST_LAUNCH_OK();
     return DDQST_OK;
