@@ -726,3 +726,20 @@ def test_large_eigensolver_line_kernel(dq, dim):
     got2 = dq.make_positive_semidefinite(dq.DensityMatrix(torch.from_numpy(rho2).cuda()))
     assert abs(dq.state_fidelity(got, got2) - fidelity_numpy(want, want2)) < 1e-6
     assert dq._lib.load().ddqst_debug_tc_status() == 0
+
+
+def test_eigensolver_bitwise_repeatable(dq):
+    """The multi-CTA eigensolver hands columns over through shared-memory inboxes and L2 mailboxes; its rotation order and arithmetic are
+    deterministic, so repeated PSD projections of one matrix must agree BIT FOR BIT (a lost or torn hand-over would not), also when
+    other sizes ran in between and left their mailbox contents behind (benchmarks/eig_stress.py runs the long version)."""
+    from benchmarks.eig_large import tomography_like
+    mats = {d: dq.DensityMatrix(torch.from_numpy(tomography_like(d, 7)[1]).cuda()) for d in (128, 256, 512)}
+    first = {}
+    for _ in range(6):
+        for d, m in mats.items():
+            out = dq.make_positive_semidefinite(m).device_tensor()
+            if d in first:
+                assert torch.equal(out, first[d]), d
+            else:
+                first[d] = out.clone()
+    assert dq._lib.load().ddqst_debug_tc_status() == 0
