@@ -10,6 +10,10 @@ from benchmarks.eig_large import tomography_like
 lib = dq._lib.load()
 raw_lib = lib
 names = ["dots", "warp+group reduce", "angle", "rotate out + send", "rotate stay", "-", "receive", "loop"]
+if os.environ.get("DDQST_JACOBI_LINE", "2") != "1":     # block kernel (default): its own phase list
+    names = ["Gram sums + reduction + angle", "local: rotation (out to the ring, stay)", "local: __syncthreads + inbox read",
+             "global step: rotation (out to the mailbox, stay)", "global step: waiting for the neighbour CTA's block", "pairs inside the blocks (per sweep)",
+             "sweep barrier", "-"]
 for _once in (0,):
     dim = int(os.environ.get("DIM", "1024"))
     _, rho = tomography_like(dim, 1)

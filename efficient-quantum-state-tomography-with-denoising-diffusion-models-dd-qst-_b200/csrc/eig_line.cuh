@@ -55,23 +55,23 @@ __device__ __forceinline__ void jl_unpack(const uint4& v, double2* x) {
 __device__ __forceinline__ void jl_unpack(const uint4& v, float2* x) {
   x[0] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y)); x[1] = make_float2(__uint_as_float(v.z), __uint_as_float(v.w));
 }
-template <typename V, int EPL> __device__ __forceinline__ void jl_get(const uint8_t* base, int t, V (&x)[EPL]) {
+template <typename V, int EPL, int TPP = 64> __device__ __forceinline__ void jl_get(const uint8_t* base, int t, V (&x)[EPL]) {
   constexpr int PER = JlChunk<V>::PER;
 #pragma unroll
-  for (int j = 0; j < EPL / PER; ++j) jl_unpack(*reinterpret_cast<const uint4*>(base + (j * 64 + t) * 16), &x[j * PER]);
+  for (int j = 0; j < EPL / PER; ++j) jl_unpack(*reinterpret_cast<const uint4*>(base + (j * TPP + t) * 16), &x[j * PER]);
 }
-template <typename V, int EPL> __device__ __forceinline__ void jl_put(uint8_t* base, int t, const V (&x)[EPL]) {
+template <typename V, int EPL, int TPP = 64> __device__ __forceinline__ void jl_put(uint8_t* base, int t, const V (&x)[EPL]) {
   constexpr int PER = JlChunk<V>::PER;
 #pragma unroll
-  for (int j = 0; j < EPL / PER; ++j) *reinterpret_cast<uint4*>(base + (j * 64 + t) * 16) = jl_pack(&x[j * PER]);
+  for (int j = 0; j < EPL / PER; ++j) *reinterpret_cast<uint4*>(base + (j * TPP + t) * 16) = jl_pack(&x[j * PER]);
 }
 // A column slice in a mailbox: the thread's W = EPL * sizeof(V) / 4 words as a stream, seven per 32-byte sector plus the tag
 // (step number) xor (the seven words); sector j of thread t at byte (j * 64 + t) * 32.
-template <typename V, int EPL> struct JlMail {
+template <typename V, int EPL, int TPP = 64> struct JlMail {
   static constexpr int WPE = (int)sizeof(V) / 4;        // words per element
   static constexpr int W = EPL * WPE;
   static constexpr int SEC = (W + 6) / 7;
-  static constexpr int BYTES = SEC * 64 * 32;
+  static constexpr int BYTES = SEC * TPP * 32;
 };
 __device__ __forceinline__ uint32_t jl_bits(double v, int half) { return half ? (uint32_t)__double2hiint(v) : (uint32_t)__double2loint(v); }
 __device__ __forceinline__ uint32_t jl_bits(float v, int) { return __float_as_uint(v); }
@@ -95,33 +95,33 @@ __device__ __forceinline__ float2 jl_elem(uint32_t w0, uint32_t w1, uint32_t, ui
 // mailbox -> column slice: fetch every sector, re-fetch the ones whose tag is not this step's.  (Measured: the hand-over is latency,
 // ~500 cycles per L2 access at gpu scope, not bandwidth; spinning on one sector first and fetching the rest afterwards costs a third
 // access.  DDQST_JL_SPIN_LAST keeps that variant for comparison.)
-template <typename V, int EPL> __device__ __forceinline__ void jl_collect(const uint8_t* mail, int t, V (&x)[EPL], uint32_t gen, int code) {
-  typedef JlMail<V, EPL> M;
+template <typename V, int EPL, int TPP = 64> __device__ __forceinline__ void jl_collect(const uint8_t* mail, int t, V (&x)[EPL], uint32_t gen, int code) {
+  typedef JlMail<V, EPL, TPP> M;
   uint32_t w[M::SEC][8];
   long long start = 0;
   uint32_t spins = 0;
   bool dead = false;
 #ifdef DDQST_JL_SPIN_LAST
-  jl_ld_sector(mail + ((M::SEC - 1) * 64 + t) * 32, w[M::SEC - 1]);
+  jl_ld_sector(mail + ((M::SEC - 1) * TPP + t) * 32, w[M::SEC - 1]);
   while (!jl_sector_ok(w[M::SEC - 1], gen)) {
     if ((++spins & 0xFFu) == 0) {
       if (start == 0) start = clock64();
       if (*((volatile int*)&g_tc_abort) != 0) { dead = true; break; }
       if (clock64() - start > 2000000000LL) { atomicCAS(&g_tc_abort, 0, code); dead = true; break; }
     }
-    jl_ld_sector(mail + ((M::SEC - 1) * 64 + t) * 32, w[M::SEC - 1]);
+    jl_ld_sector(mail + ((M::SEC - 1) * TPP + t) * 32, w[M::SEC - 1]);
   }
 #pragma unroll
-  for (int j = 0; j < M::SEC - 1; ++j) jl_ld_sector(mail + (j * 64 + t) * 32, w[j]);
+  for (int j = 0; j < M::SEC - 1; ++j) jl_ld_sector(mail + (j * TPP + t) * 32, w[j]);
 #else
 #pragma unroll
-  for (int j = 0; j < M::SEC; ++j) jl_ld_sector(mail + (j * 64 + t) * 32, w[j]);
+  for (int j = 0; j < M::SEC; ++j) jl_ld_sector(mail + (j * TPP + t) * 32, w[j]);
 #endif
   while (!dead) {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < M::SEC; ++j)
-      if (!jl_sector_ok(w[j], gen)) { ok = false; jl_ld_sector(mail + (j * 64 + t) * 32, w[j]); }
+      if (!jl_sector_ok(w[j], gen)) { ok = false; jl_ld_sector(mail + (j * TPP + t) * 32, w[j]); }
     if (ok) break;
     if ((++spins & 0xFFu) == 0) {
       if (start == 0) start = clock64();
@@ -195,7 +195,7 @@ template <typename R> __device__ __forceinline__ R jl_reduce4(R v0, R v1, R v2, 
 // Rotation, first half: the outgoing column, straight to its destination (DST 0: shared-memory inbox / park slot, DST 1: mailbox).
 //   ODD  step (lower = P, upper = Q):  Q <- Q p;  out = c P - s Q   (rotated lower -> upper position -> right neighbour)
 //   EVEN step (lower = Q, upper = P):  P <- P p;  out = s Q + c P   (rotated upper -> lower position -> left neighbour)
-template <bool ODD, int DST, bool SWAP, typename V, typename R, int EPL>
+template <bool ODD, int DST, bool SWAP, typename V, typename R, int EPL, int TPP = 64>
 __device__ __forceinline__ void jl_rotate_out(V (&P)[EPL], V (&Q)[EPL], R c, R s, R pr, R pi, uint8_t* dst, int t, uint32_t gen) {
 #pragma unroll
   for (int e = 0; e < EPL; ++e) {
@@ -216,10 +216,10 @@ __device__ __forceinline__ void jl_rotate_out(V (&P)[EPL], V (&Q)[EPL], R c, R s
       V o[PER];
 #pragma unroll
       for (int i = 0; i < PER; ++i) { o[i].x = out(j * PER + i, 0); o[i].y = out(j * PER + i, 1); }
-      *reinterpret_cast<uint4*>(dst + (j * 64 + t) * 16) = jl_pack(o);
+      *reinterpret_cast<uint4*>(dst + (j * TPP + t) * 16) = jl_pack(o);
     }
   } else {
-    typedef JlMail<V, EPL> M;
+    typedef JlMail<V, EPL, TPP> M;
 #pragma unroll
     for (int j = 0; j < M::SEC; ++j) {
       uint32_t w[8];
@@ -236,7 +236,7 @@ __device__ __forceinline__ void jl_rotate_out(V (&P)[EPL], V (&Q)[EPL], R c, R s
         tag ^= w[i];
       }
       w[7] = tag;
-      jl_st_sector(dst + (j * 64 + t) * 32, w);
+      jl_st_sector(dst + (j * TPP + t) * 32, w);
     }
   }
 }
@@ -455,7 +455,7 @@ static int launch_jacobi_line(typename JlVec<R>::V* GT, int n, int max_sweeps, R
 // only the fourth local step applies the line rule -- swap, lower block to the left neighbour CTA after even block steps, upper block
 // to the right after odd ones -- through the mailboxes, so three steps in four never leave the SM.  n/4 block steps bring every pair
 // of blocks together once; pairs inside a block are rotated once per sweep, at its start, out of shared memory.
-template <typename V, typename R, int EPL>
+template <typename V, typename R, int EPL, int TPP = 64>
 __device__ __forceinline__ bool jl_pair_angle(const V (&P)[EPL], const V (&Q)[EPL], R carry, bool odd, R* rp, int lane, int wig, int grp,
                                               R tol, R& cc, R& ss, R& pr, R& pi, float& worst) {
   R q0 = 0, q1 = 0, r0 = 0, r1 = 0, i0 = 0, i1 = 0;                      // |Q|^2 and d = conj(P) . Q, two accumulators each
@@ -469,23 +469,29 @@ __device__ __forceinline__ bool jl_pair_angle(const V (&P)[EPL], const V (&Q)[EP
     i1 += P[e + 1].x * Q[e + 1].y - P[e + 1].y * Q[e + 1].x;
   }
   const R tot = jl_reduce4<R>(carry, q0 + q1, r0 + r1, i0 + i1, lane);
-  if ((lane & 7) == 0) rp[wig * 4 + (lane >> 3)] = tot;
-  jl_bar_sync(1 + grp, 64);
-  const R np = rp[0] + rp[4], nq = rp[1] + rp[5], dr = rp[2] + rp[6], di = rp[3] + rp[7];
+  R np, nq, dr, di;
+  if (TPP == 32) {                                      // one warp per pair: the four totals sit in lanes 0 / 8 / 16 / 24
+    np = __shfl_sync(0xFFFFFFFFu, tot, 0); nq = __shfl_sync(0xFFFFFFFFu, tot, 8);
+    dr = __shfl_sync(0xFFFFFFFFu, tot, 16); di = __shfl_sync(0xFFFFFFFFu, tot, 24);
+  } else {
+    if ((lane & 7) == 0) rp[wig * 4 + (lane >> 3)] = tot;
+    jl_bar_sync(1 + grp, 64);
+    np = rp[0] + rp[4]; nq = rp[1] + rp[5]; dr = rp[2] + rp[6]; di = rp[3] + rp[7];
+  }
   const R sa = odd ? np : nq, sb = odd ? nq : np, gr = dr, gi = odd ? di : -di;
   worst = fmaxf(worst, (float)((gr * gr + gi * gi) / (sa * sb)));
   cc = 1; ss = 0; pr = 1; pi = 0;
   return jl_angle(sa, sb, gr, gi, tol, cc, ss, pr, pi);
 }
 
-template <typename R, int EPL, int G>
-__global__ void __launch_bounds__(64 * G, 1) jacobi_block_kernel(typename JlVec<R>::V* __restrict__ GT, int n, int max_sweeps, R tol,
+template <typename R, int EPL, int G, int TPP>
+__global__ void __launch_bounds__(TPP * G, 1) jacobi_block_kernel(typename JlVec<R>::V* __restrict__ GT, int n, int max_sweeps, R tol,
                                                                      JacobiCtl* ctl, uint8_t* __restrict__ comm0, uint8_t* __restrict__ comm1) {
   typedef typename JlVec<R>::V V;
   extern __shared__ __align__(16) uint8_t jl_smem[];
-  constexpr int COLB = EPL * 64 * (int)sizeof(V);
-  constexpr int MAILB = JlMail<V, EPL>::BYTES;
-  const int tid = threadIdx.x, grp = tid >> 6, t = tid & 63, lane = tid & 31, wig = (tid >> 5) & 1;
+  constexpr int COLB = EPL * TPP * (int)sizeof(V);
+  constexpr int MAILB = JlMail<V, EPL, TPP>::BYTES;
+  const int tid = threadIdx.x, grp = tid / TPP, t = tid % TPP, lane = tid & 31, wig = t >> 5;
   const int c = blockIdx.x, nc = gridDim.x;
   const bool first = c == 0, last = c == nc - 1;
   // G columns per block (G groups of 64 threads per CTA; G = 4, or 8 for the latency-bound small n where a global hand-over every
@@ -498,44 +504,51 @@ __global__ void __launch_bounds__(64 * G, 1) jacobi_block_kernel(typename JlVec<
   auto mail = [&](int dir, int cta) { return (dir ? comm1 : comm0) + (size_t)(cta * G + grp) * MAILB; };
 
   V P[EPL], Q[EPL];                                     // block step 0 is even: lower block = the Q columns, upper block = the P columns
-  jl_get<V, EPL>(reinterpret_cast<const uint8_t*>(GT + (int64_t)(2 * G * c + grp) * n), t, Q);
-  jl_get<V, EPL>(reinterpret_cast<const uint8_t*>(GT + (int64_t)(2 * G * c + G + grp) * n), t, P);
+  jl_get<V, EPL, TPP>(reinterpret_cast<const uint8_t*>(GT + (int64_t)(2 * G * c + grp) * n), t, Q);
+  jl_get<V, EPL, TPP>(reinterpret_cast<const uint8_t*>(GT + (int64_t)(2 * G * c + G + grp) * n), t, P);
   R carry = 0;
   uint32_t rc = 0;                                      // reduction-scratch parity
   int sweep = 0;
   uint32_t gb = 0;                                      // block steps so far (mailbox generation)
   const int nblk = n / G;
+#ifdef DDQST_JL_PROFILE
+  const int jl_watch = (c == 5 && grp == 1) ? 0 : (c == 5 && grp == 3) ? 1 : -1;
+  long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long _t0 = clock64();
+#endif
   for (; sweep < max_sweeps; ++sweep) {
     int rot = 0;
     float worst = 0.f;
+    JL_STAMP(7);
     // ---- pairs inside the two resident blocks: G-1 rounds of a round-robin tournament (circle method) out of shared memory,
     //      block grp / (G/2), pair grp % (G/2)
-    jl_put<V, EPL>(slot(grp), t, Q);
-    jl_put<V, EPL>(slot(G + grp), t, P);
+    jl_put<V, EPL, TPP>(slot(grp), t, Q);
+    jl_put<V, EPL, TPP>(slot(G + grp), t, P);
     __syncthreads();
 #pragma unroll 1
     for (int r = 0; r < G - 1; ++r) {
       const int blk = grp / (G / 2), k = grp % (G / 2);
       int i = k == 0 ? G - 1 : (r + k) % (G - 1), j = k == 0 ? r : (r + (G - 1) - k) % (G - 1);
       if (i > j) { const int tmp = i; i = j; j = tmp; }
-      jl_get<V, EPL>(slot(blk * G + i), t, P);
-      jl_get<V, EPL>(slot(blk * G + j), t, Q);
+      jl_get<V, EPL, TPP>(slot(blk * G + i), t, P);
+      jl_get<V, EPL, TPP>(slot(blk * G + j), t, Q);
       R np = 0;
 #pragma unroll
       for (int e = 0; e < EPL; ++e) np += P[e].x * P[e].x + P[e].y * P[e].y;
       R cc, ss, pr, pi;
-      if (jl_pair_angle<V, R, EPL>(P, Q, np, true, red + (rc++ & 1u) * 8, lane, wig, grp, tol, cc, ss, pr, pi, worst)) ++rot;
-      jl_rotate_out<true, 0, false, V, R, EPL>(P, Q, cc, ss, pr, pi, slot(blk * G + j), t, 0u);
+      if (jl_pair_angle<V, R, EPL, TPP>(P, Q, np, true, red + (rc++ & 1u) * 8, lane, wig, grp, tol, cc, ss, pr, pi, worst)) ++rot;
+      jl_rotate_out<true, 0, false, V, R, EPL, TPP>(P, Q, cc, ss, pr, pi, slot(blk * G + j), t, 0u);
       (void)jl_rotate_stay<true, false, V, R, EPL>(P, Q, cc, ss);
-      jl_put<V, EPL>(slot(blk * G + i), t, P);
+      jl_put<V, EPL, TPP>(slot(blk * G + i), t, P);
       __syncthreads();
     }
-    jl_get<V, EPL>(slot(grp), t, Q);
-    jl_get<V, EPL>(slot(G + grp), t, P);
+    jl_get<V, EPL, TPP>(slot(grp), t, Q);
+    jl_get<V, EPL, TPP>(slot(G + grp), t, P);
     carry = 0;
 #pragma unroll
     for (int e = 0; e < EPL; ++e) carry += P[e].x * P[e].x + P[e].y * P[e].y;
     __syncthreads();                                    // the slots turn back into inboxes
+    JL_STAMP(5);
     // ---- block steps
     uint32_t lp = 0;                                    // local inbox parity
 #pragma unroll 1
@@ -545,31 +558,36 @@ __global__ void __launch_bounds__(64 * G, 1) jacobi_block_kernel(typename JlVec<
 #pragma unroll 1
         for (int ls = 0; ls < G; ++ls) {
           R cc, ss, pr, pi;
-          if (jl_pair_angle<V, R, EPL>(P, Q, carry, odd, red + (rc++ & 1u) * 8, lane, wig, grp, tol, cc, ss, pr, pi, worst)) ++rot;
+          if (jl_pair_angle<V, R, EPL, TPP>(P, Q, carry, odd, red + (rc++ & 1u) * 8, lane, wig, grp, tol, cc, ss, pr, pi, worst)) ++rot;
+          JL_STAMP(0);
           if (ls < G - 1) {
             uint8_t* dst = slot(((grp + G - 1) % G) * 2 + (int)lp);  // the rotated Q moves on to group i-1
-            if (odd) { jl_rotate_out<true, 0, false, V, R, EPL>(P, Q, cc, ss, pr, pi, dst, t, 0u); carry = jl_rotate_stay<true, false, V, R, EPL>(P, Q, cc, ss); }
-            else { jl_rotate_out<false, 0, false, V, R, EPL>(P, Q, cc, ss, pr, pi, dst, t, 0u); carry = jl_rotate_stay<false, false, V, R, EPL>(P, Q, cc, ss); }
+            if (odd) { jl_rotate_out<true, 0, false, V, R, EPL, TPP>(P, Q, cc, ss, pr, pi, dst, t, 0u); carry = jl_rotate_stay<true, false, V, R, EPL>(P, Q, cc, ss); }
+            else { jl_rotate_out<false, 0, false, V, R, EPL, TPP>(P, Q, cc, ss, pr, pi, dst, t, 0u); carry = jl_rotate_stay<false, false, V, R, EPL>(P, Q, cc, ss); }
+            JL_STAMP(1);
             __syncthreads();
-            jl_get<V, EPL>(slot(grp * 2 + (int)lp), t, Q);
+            jl_get<V, EPL, TPP>(slot(grp * 2 + (int)lp), t, Q);
             lp ^= 1u;
+            JL_STAMP(2);
           } else if (odd) {                             // upper block -> right neighbour
-            jl_rotate_out<true, 1, true, V, R, EPL>(P, Q, cc, ss, pr, pi, mail(0, c + 1), t, gb + 1u);
+            jl_rotate_out<true, 1, true, V, R, EPL, TPP>(P, Q, cc, ss, pr, pi, mail(0, c + 1), t, gb + 1u);
             carry = jl_rotate_stay<true, true, V, R, EPL>(P, Q, cc, ss);
           } else {                                      // lower block -> left neighbour (CTA 0 parks it)
-            if (first) jl_rotate_out<false, 0, true, V, R, EPL>(P, Q, cc, ss, pr, pi, slot(2 * G + grp), t, 0u);
-            else jl_rotate_out<false, 1, true, V, R, EPL>(P, Q, cc, ss, pr, pi, mail(1, c - 1), t, gb + 1u);
+            if (first) jl_rotate_out<false, 0, true, V, R, EPL, TPP>(P, Q, cc, ss, pr, pi, slot(2 * G + grp), t, 0u);
+            else jl_rotate_out<false, 1, true, V, R, EPL, TPP>(P, Q, cc, ss, pr, pi, mail(1, c - 1), t, gb + 1u);
             carry = jl_rotate_stay<false, true, V, R, EPL>(P, Q, cc, ss);
           }
         }
       }
+      JL_STAMP(3);
       // the arriving block
       if (!odd) {
-        if (!last) jl_collect<V, EPL>(mail(1, c), t, Q, gb + 1u, 71);
+        if (!last) jl_collect<V, EPL, TPP>(mail(1, c), t, Q, gb + 1u, 71);
       } else {
-        if (first) jl_get<V, EPL>(slot(2 * G + grp), t, Q);          // every thread reads back exactly the chunks it wrote
-        else jl_collect<V, EPL>(mail(0, c), t, Q, gb + 1u, 72);
+        if (first) jl_get<V, EPL, TPP>(slot(2 * G + grp), t, Q);          // every thread reads back exactly the chunks it wrote
+        else jl_collect<V, EPL, TPP>(mail(0, c), t, Q, gb + 1u, 72);
       }
+      JL_STAMP(4);
     }
     if (t == 0) {
       if (rot > 0) atomicAdd(&ctl->rotations[sweep], rot);
@@ -592,37 +610,42 @@ __global__ void __launch_bounds__(64 * G, 1) jacobi_block_kernel(typename JlVec<
       __threadfence();
     }
     __syncthreads();
+    JL_STAMP(6);
     const int total = __ldcg(&ctl->rotations[sweep]);
     if (total == 0) { ++sweep; break; }
     if (sweep < 48 && __uint_as_float(__ldcg(&ctl->max_ratio2[sweep])) < __ldcg(&ctl->stop_ratio2)) { ++sweep; break; }
     if (*((volatile int*)&g_tc_abort) != 0) { ++sweep; break; }
   }
-  jl_put<V, EPL>(reinterpret_cast<uint8_t*>(GT + (int64_t)(2 * G * c + grp) * n), t, Q);
-  jl_put<V, EPL>(reinterpret_cast<uint8_t*>(GT + (int64_t)(2 * G * c + G + grp) * n), t, P);
+#ifdef DDQST_JL_PROFILE
+  if (jl_watch >= 0 && t == 0)
+    for (int i = 0; i < 8; ++i) g_jl_prof[jl_watch * 16 + i] += _acc[i];
+#endif
+  jl_put<V, EPL, TPP>(reinterpret_cast<uint8_t*>(GT + (int64_t)(2 * G * c + grp) * n), t, Q);
+  jl_put<V, EPL, TPP>(reinterpret_cast<uint8_t*>(GT + (int64_t)(2 * G * c + G + grp) * n), t, P);
   if (c == 0 && tid == 0) ctl->sweeps_done = sweep;
 }
 
-template <typename R, int EPL, int G = 4>
+template <typename R, int EPL, int G = 4, int TPP = 64>
 static int launch_jacobi_block(typename JlVec<R>::V* GT, int n, int max_sweeps, R tol, JacobiCtl* ctl, uint8_t* comm0, int64_t bytes0,
                                uint8_t* comm1, int64_t bytes1, cudaStream_t s, bool* launched) {
   typedef typename JlVec<R>::V V;
-  constexpr int COLB = EPL * 64 * (int)sizeof(V);
+  constexpr int COLB = EPL * TPP * (int)sizeof(V);
   constexpr int smem = 3 * G * COLB + G * 16 * (int)sizeof(R) + 16;
   *launched = false;
-  if (n != EPL * 64 || n % (2 * G) != 0 || n / (2 * G) < 2) return DDQST_OK;
+  if (n != EPL * TPP || n % (2 * G) != 0 || n / (2 * G) < 2) return DDQST_OK;
   const int nc = n / (2 * G);
-  const int64_t need = (int64_t)nc * G * JlMail<V, EPL>::BYTES;
+  const int64_t need = (int64_t)nc * G * JlMail<V, EPL, TPP>::BYTES;
   if (comm0 == nullptr || comm1 == nullptr || bytes0 < need || bytes1 < need) return DDQST_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(jacobi_block_kernel<R, EPL, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(jacobi_block_kernel<R, EPL, G, TPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       (void)cudaGetLastError();
       return DDQST_OK;
     }
     attr_set = true;
   }
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_block_kernel<R, EPL, G>, 64 * G, smem) != cudaSuccess ||
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_block_kernel<R, EPL, G, TPP>, TPP * G, smem) != cudaSuccess ||
       (int64_t)per_sm * num_sms() < nc) {
     (void)cudaGetLastError();
     return DDQST_OK;
@@ -631,7 +654,7 @@ static int launch_jacobi_block(typename JlVec<R>::V* GT, int n, int max_sweeps, 
   DDQST_CUDA_OK(cudaMemsetAsync(comm1, 0, (size_t)need, s));
   DDQST_CUDA_OK(cudaMemsetAsync(&ctl->sweep_barrier, 0, sizeof(unsigned int), s));
   void* args[] = {&GT, &n, &max_sweeps, &tol, &ctl, &comm0, &comm1};
-  DDQST_CUDA_OK(cudaLaunchCooperativeKernel((void*)jacobi_block_kernel<R, EPL, G>, dim3((unsigned)nc), dim3(64 * G), args, smem, s));
+  DDQST_CUDA_OK(cudaLaunchCooperativeKernel((void*)jacobi_block_kernel<R, EPL, G, TPP>, dim3((unsigned)nc), dim3(TPP * G), args, smem, s));
   *launched = true;
   return DDQST_OK;
 }

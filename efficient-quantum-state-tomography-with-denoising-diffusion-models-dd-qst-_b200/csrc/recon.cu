@@ -1343,7 +1343,10 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
       } else if (small_block) {
         uint8_t* c0 = (uint8_t*)VT;
         uint8_t* c1 = c0 + 8 * nn;
-        if (small_env != 2) {
+        if (small_env == 3) {                           // one warp per pair, blocks of 8 columns
+          if (n == 128) DDQST_TRY((launch_jacobi_block<float, 4, 8, 32>(G32, n, 20, 1e-7f, c32, c0, 8 * nn, c1, 8 * nn, s, &f32_done)));
+          else DDQST_TRY((launch_jacobi_block<float, 8, 8, 32>(G32, n, 20, 1e-7f, c32, c0, 8 * nn, c1, 8 * nn, s, &f32_done)));
+        } else if (small_env != 2) {
           if (n == 128) DDQST_TRY((launch_jacobi_block<float, 2, 4>(G32, n, 20, 1e-7f, c32, c0, 8 * nn, c1, 8 * nn, s, &f32_done)));
           else DDQST_TRY((launch_jacobi_block<float, 4, 4>(G32, n, 20, 1e-7f, c32, c0, 8 * nn, c1, 8 * nn, s, &f32_done)));
         } else {
@@ -1373,7 +1376,10 @@ static int jacobi_eigh(const double2* A, int n, double* evals, double2* VT, char
   if (small_block && GT != (double2*)ws) {
     uint8_t* c0 = (uint8_t*)VT;
     uint8_t* c1 = (uint8_t*)ws;
-    if (small_env != 2) {
+    if (small_env == 3) {
+      if (n == 128) DDQST_TRY((launch_jacobi_block<double, 4, 8, 32>(GT, n, max_sweeps, tol, ctl, c0, 16 * nn, c1, 16 * nn, s, &ring_done)));
+      else DDQST_TRY((launch_jacobi_block<double, 8, 8, 32>(GT, n, max_sweeps, tol, ctl, c0, 16 * nn, c1, 16 * nn, s, &ring_done)));
+    } else if (small_env != 2) {
       if (n == 128) DDQST_TRY((launch_jacobi_block<double, 2, 4>(GT, n, max_sweeps, tol, ctl, c0, 16 * nn, c1, 16 * nn, s, &ring_done)));
       else DDQST_TRY((launch_jacobi_block<double, 4, 4>(GT, n, max_sweeps, tol, ctl, c0, 16 * nn, c1, 16 * nn, s, &ring_done)));
     } else {
