@@ -116,7 +116,7 @@ def main():
         report(f"fidelity_pure N={N}", 16 * dim * dim, ms)
         r2 = torch.eye(dim, dtype=torch.complex128, device=dev) / dim + 1e-3 * torch.randn(dim, dim, dtype=torch.complex128, device=dev)
         r2 = (r2 + r2.conj().T) / 2
-        wsp = torch.empty(2 * 16 * dim * dim + 8 * dim + 4096, dtype=torch.uint8, device=dev)
+        wsp = torch.empty(2 * 16 * dim * dim + 8 * dim + 1024 + 24 * dim * dim + 4096, dtype=torch.uint8, device=dev)   # + the mixed-precision scratch
         work = r2.clone()
 
         def psd():
