@@ -173,13 +173,20 @@ __global__ void __launch_bounds__(128) histogram_private_kernel(const T* __restr
 // N <= 8, second form: K interleaved 32-bit copies of the bins per warp, lane l adding into copy l % K with a fire-and-forget
 // shared-memory atomic (word = bin * K + copy).  One instruction per shot and no load -> add -> store chain to wait for, against
 // LDS / IADD / STS of the private-counter kernel; two lanes collide only when they share the copy AND their bins fall on the same bank.
-template <typename T, int K>
-__global__ void __launch_bounds__(256) histogram_copies_kernel(const T* __restrict__ data, int64_t n, int nbins, uint32_t* __restrict__ hist) {
+// SHARED: one set of copies per CTA instead of per warp (they are atomics, so warps may share): K can grow to 32 -- no two lanes of a
+// warp on one word -- while many more warps fit an SM.
+template <typename T, int K, bool SHARED = false>
+__global__ void __launch_bounds__(SHARED ? 512 : 256) histogram_copies_kernel(const T* __restrict__ data, int64_t n, int nbins, uint32_t* __restrict__ hist) {
   extern __shared__ __align__(16) uint32_t hsh[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t* w = hsh + (size_t)warp * nbins * K;
-  for (int i = lane; i < nbins * K; i += 32) w[i] = 0;
-  __syncwarp();
+  uint32_t* w = SHARED ? hsh : hsh + (size_t)warp * nbins * K;
+  if (SHARED) {
+    for (int i = threadIdx.x; i < nbins * K; i += blockDim.x) w[i] = 0;
+    __syncthreads();
+  } else {
+    for (int i = lane; i < nbins * K; i += 32) w[i] = 0;
+    __syncwarp();
+  }
   constexpr int VEC = 16 / sizeof(T);
   const int64_t nvec = n / VEC;
   const uint4* v4 = reinterpret_cast<const uint4*>(data);
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(256) histogram_copies_kernel(const T* __restri
       }
     }
   };
-  constexpr int DEPTH = 4;
+  constexpr int DEPTH = 4;               // 8 loads in flight cost the 32-register budget that 4 CTAs x 512 threads per SM need (measured 2.3 TB/s)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint4 buf[DEPTH];
@@ -222,12 +229,140 @@ __global__ void __launch_bounds__(256) histogram_copies_kernel(const T* __restri
   }
   if (blockIdx.x == 0)
     for (int64_t j = nvec * VEC + threadIdx.x; j < n; j += blockDim.x) atomicAdd(hist + ((uint32_t)data[j] & mask_bins), 1u);
+  if (SHARED) {
+    __syncthreads();
+    for (int bin = threadIdx.x; bin < nbins; bin += blockDim.x) {
+      uint32_t sum = 0;
+#pragma unroll
+      for (int c = 0; c < K; ++c) sum += w[bin * K + ((c + lane) & (K - 1))];
+      if (sum) atomicAdd(hist + bin, sum);
+    }
+    return;
+  }
   __syncwarp();
   for (int bin = lane; bin < nbins; bin += 32) {
     uint32_t sum = 0;
 #pragma unroll
     for (int c = 0; c < K; ++c) sum += w[bin * K + ((c + lane) & (K - 1))];
     if (sum) atomicAdd(hist + bin, sum);
+  }
+}
+
+// N <= 8, third form: both of the above in one CTA.  The interleaved-copies kernel is bound by the shared-ATOMIC rate (~8 shots/clk/SM), the
+// private-counter kernel by its LDS -> IADD -> STS chain (~5): warps 0-3 run private 16-bit counters on the first `cut` vectors, warps 4-7
+// fire-and-forget atomics into 8 interleaved copies on the rest, so that both units work at once.
+template <typename T>
+__global__ void __launch_bounds__(256) histogram_hybrid_kernel(const T* __restrict__ data, int64_t n, int nbins, uint32_t* __restrict__ hist,
+                                                               int64_t cut) {
+  extern __shared__ __align__(16) uint8_t hyb[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int DEPTH = 4;
+  const int64_t nvec = n / VEC;
+  const uint4* v4 = reinterpret_cast<const uint4*>(data);
+  const uint32_t mask_bins = (uint32_t)nbins - 1u;
+  auto load16 = [&](int64_t i) {
+    uint4 q;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(v4 + i));
+    return q;
+  };
+  if (warp < 4) {
+    // ---- private 16-bit counters, [bin >> 1][lane] words (histogram_private_kernel)
+    uint8_t* wbase = hyb + warp * 16384;
+    uint8_t* mine = wbase + lane * 4;
+    uint32_t* w32 = reinterpret_cast<uint32_t*>(wbase);
+    for (int i = lane; i < 4096; i += 32) w32[i] = 0;
+    __syncwarp();
+    auto bump = [&](uint32_t bin) {
+      uint16_t* c = reinterpret_cast<uint16_t*>(mine + ((bin >> 1) << 7) + ((bin & 1u) << 1));
+      *c = (uint16_t)(*c + 1);
+    };
+    auto fold = [&]() {
+      __syncwarp();
+      for (int b0 = 0; b0 < nbins; b0 += 32) {
+        uint32_t bin = b0 + lane, sum = 0;
+        if ((int)bin < nbins) {
+          for (int it = 0; it < 32; ++it) {
+            int l2 = (lane + it) & 31;
+            sum += *reinterpret_cast<uint16_t*>(wbase + l2 * 4 + ((bin >> 1) << 7) + ((bin & 1u) << 1));
+          }
+          if (sum) atomicAdd(hist + bin, sum);
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < 4096; i += 32) w32[i] = 0;
+      __syncwarp();
+    };
+    int since_fold = 0;
+    const int64_t stride = (int64_t)gridDim.x * 128;
+    int64_t i = (int64_t)blockIdx.x * 128 + warp * 32 + lane;
+    uint4 buf[DEPTH];
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) buf[d] = (i + d * stride < cut) ? load16(i + d * stride) : make_uint4(0, 0, 0, 0);
+    for (; i < cut; i += DEPTH * stride) {
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d) {
+        const int64_t cur = i + d * stride;
+        if (cur >= cut) break;
+        const uint4 q = buf[d];
+        const int64_t nxt = cur + DEPTH * stride;
+        if (nxt < cut) buf[d] = load16(nxt);
+        const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t x = words[k];
+          if (sizeof(T) == 1) { bump(x & mask_bins); bump((x >> 8) & mask_bins); bump((x >> 16) & mask_bins); bump((x >> 24) & mask_bins); }
+          else { bump(x & mask_bins); bump((x >> 16) & mask_bins); }
+        }
+        if (++since_fold >= 65535 / VEC - DEPTH) {
+          if (__activemask() == 0xFFFFFFFFu) { fold(); since_fold = 0; }
+        }
+      }
+    }
+    __syncwarp();
+    fold();
+  } else {
+    // ---- 8 interleaved 32-bit copies, fire-and-forget atomics (histogram_copies_kernel)
+    constexpr int K = 8;
+    uint32_t* w = reinterpret_cast<uint32_t*>(hyb + 4 * 16384) + (size_t)(warp - 4) * nbins * K;
+    for (int i = lane; i < nbins * K; i += 32) w[i] = 0;
+    __syncwarp();
+    uint32_t* mine = w + (lane & (K - 1));
+    const int64_t stride = (int64_t)gridDim.x * 128;
+    int64_t i = cut + (int64_t)blockIdx.x * 128 + (warp - 4) * 32 + lane;
+    uint4 buf[DEPTH];
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) buf[d] = (i + d * stride < nvec) ? load16(i + d * stride) : make_uint4(0, 0, 0, 0);
+    for (; i < nvec; i += DEPTH * stride) {
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d) {
+        const int64_t cur = i + d * stride;
+        if (cur >= nvec) break;
+        const uint4 q = buf[d];
+        const int64_t nxt = cur + DEPTH * stride;
+        if (nxt < nvec) buf[d] = load16(nxt);
+        const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t x = words[k];
+          if (sizeof(T) == 1) {
+            atomicAdd(mine + ((x & mask_bins) * K), 1u); atomicAdd(mine + (((x >> 8) & mask_bins) * K), 1u);
+            atomicAdd(mine + (((x >> 16) & mask_bins) * K), 1u); atomicAdd(mine + (((x >> 24) & mask_bins) * K), 1u);
+          } else {
+            atomicAdd(mine + ((x & mask_bins) * K), 1u); atomicAdd(mine + (((x >> 16) & mask_bins) * K), 1u);
+          }
+        }
+      }
+    }
+    if (blockIdx.x == 0 && warp == 4)
+      for (int64_t j = nvec * VEC + lane; j < n; j += 32) atomicAdd(hist + ((uint32_t)data[j] & mask_bins), 1u);
+    __syncwarp();
+    for (int bin = lane; bin < nbins; bin += 32) {
+      uint32_t sum = 0;
+#pragma unroll
+      for (int c = 0; c < K; ++c) sum += w[bin * K + ((c + lane) & (K - 1))];
+      if (sum) atomicAdd(hist + bin, sum);
+    }
   }
 }
 
@@ -1516,10 +1651,49 @@ int ddqst_histogram(const void* packed, int elem_bytes, int64_t n, int32_t num_q
   DDQST_REQUIRE(((uintptr_t)packed & 15) == 0, DDQST_EINVAL_SHAPE, "packed bitstrings must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   const int nbins = 1 << num_qubits;
-  // DDQST_HIST_COPIES: 8 (default) = interleaved copies per warp + fire-and-forget shared atomics (8 copies up to 256 bins, 4 at 512,
-  // 2 at 1024: 8 KB per warp); 0 = private 16-bit counters; 1 = private counters bumped by one atomic; 2 / 4 / 16 = that many copies
+  // DDQST_HIST_COPIES: 32 (default) = interleaved copies per CTA + fire-and-forget shared atomics; 2 / 4 / 8 / 16 = that many copies per
+  // WARP; 0 = private 16-bit counters; 1 = private counters bumped by one atomic; 100 + p = hybrid with p % of the data on private warps;
+  // 208 / 216 = 8 / 16 copies per CTA
   static int copies_env = -1;
-  if (copies_env < 0) { const char* e = getenv("DDQST_HIST_COPIES"); copies_env = e ? atoi(e) : 8; }
+  if (copies_env < 0) { const char* e = getenv("DDQST_HIST_COPIES"); copies_env = e ? atoi(e) : 32; }
+  if (num_qubits <= 10 && (copies_env == 32 || copies_env == 208 || copies_env == 216 || copies_env == 232)) {
+    // per-CTA shared copies, 512 threads, 4 CTAs per SM: 32 copies up to 256 bins (lane-private words: conflict free), 16 at 512, 8 at 1024
+    const int64_t nv = n / (16 / elem_bytes);
+    int K = copies_env >= 200 ? copies_env - 200 : 32;
+    while (K > 8 && nbins * K > 8192) K >>= 1;
+    const int smem = nbins * K * 4;
+    int64_t want_s = (nv + 511) / 512;
+    int grid_s = (int)(want_s < 1 ? 1 : want_s > (int64_t)num_sms() * 4 ? (int64_t)num_sms() * 4 : want_s);
+#define DDQST_HIST_SHARED_LAUNCH(TT, KK)                                                                                                   \
+    do {                                                                                                                                  \
+      DDQST_CUDA_OK(cudaFuncSetAttribute(histogram_copies_kernel<TT, KK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
+      histogram_copies_kernel<TT, KK, true><<<grid_s, 512, smem, s>>>((const TT*)packed, n, nbins, hist);                                 \
+    } while (0)
+    if (elem_bytes == 1) {
+      if (K == 8) DDQST_HIST_SHARED_LAUNCH(uint8_t, 8); else if (K == 16) DDQST_HIST_SHARED_LAUNCH(uint8_t, 16); else DDQST_HIST_SHARED_LAUNCH(uint8_t, 32);
+    } else {
+      if (K == 8) DDQST_HIST_SHARED_LAUNCH(uint16_t, 8); else if (K == 16) DDQST_HIST_SHARED_LAUNCH(uint16_t, 16); else DDQST_HIST_SHARED_LAUNCH(uint16_t, 32);
+    }
+#undef DDQST_HIST_SHARED_LAUNCH
+    DDQST_LAUNCH_OK();
+    return DDQST_OK;
+  }
+  if (num_qubits <= 8 && copies_env >= 100 && copies_env < 200) {        // hybrid: DDQST_HIST_COPIES = 100 + percent of the vectors for the private warps
+    const int64_t nv = n / (16 / elem_bytes);
+    const int64_t cut = nv * (copies_env - 100) / 100;
+    const int smem = 4 * 16384 + 4 * nbins * 8 * 4;
+    int64_t want_h = (nv + 255) / 256;
+    int grid_h = (int)(want_h < 1 ? 1 : want_h > (int64_t)num_sms() * 2 ? (int64_t)num_sms() * 2 : want_h);
+    if (elem_bytes == 1) {
+      DDQST_CUDA_OK(cudaFuncSetAttribute(histogram_hybrid_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      histogram_hybrid_kernel<uint8_t><<<grid_h, 256, smem, s>>>((const uint8_t*)packed, n, nbins, hist, cut);
+    } else {
+      DDQST_CUDA_OK(cudaFuncSetAttribute(histogram_hybrid_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      histogram_hybrid_kernel<uint16_t><<<grid_h, 256, smem, s>>>((const uint16_t*)packed, n, nbins, hist, cut);
+    }
+    DDQST_LAUNCH_OK();
+    return DDQST_OK;
+  }
   if (num_qubits <= 10 && (copies_env == 2 || copies_env == 4 || copies_env == 8 || copies_env == 16)) {
     const int64_t nv = n / (16 / elem_bytes);
     int K = copies_env;
