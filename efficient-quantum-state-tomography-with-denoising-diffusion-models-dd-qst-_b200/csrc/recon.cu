@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(128) histogram_private_kernel(const T* __restr
 // SHARED: one set of copies per CTA instead of per warp (they are atomics, so warps may share): K can grow to 32 -- no two lanes of a
 // warp on one word -- while many more warps fit an SM.
 template <typename T, int K, bool SHARED = false>
-__global__ void __launch_bounds__(SHARED ? 512 : 256) histogram_copies_kernel(const T* __restrict__ data, int64_t n, int nbins, uint32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(SHARED ? 512 : 256, SHARED ? 2 : 1) histogram_copies_kernel(const T* __restrict__ data, int64_t n, int nbins, uint32_t* __restrict__ hist) {
   extern __shared__ __align__(16) uint32_t hsh[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* w = SHARED ? hsh : hsh + (size_t)warp * nbins * K;
@@ -1657,13 +1657,15 @@ int ddqst_histogram(const void* packed, int elem_bytes, int64_t n, int32_t num_q
   static int copies_env = -1;
   if (copies_env < 0) { const char* e = getenv("DDQST_HIST_COPIES"); copies_env = e ? atoi(e) : 32; }
   if (num_qubits <= 10 && (copies_env == 32 || copies_env == 208 || copies_env == 216 || copies_env == 232)) {
-    // per-CTA shared copies, 512 threads, 4 CTAs per SM: 32 copies up to 256 bins (lane-private words: conflict free), 16 at 512, 8 at 1024
+    // per-CTA shared copies, 512 threads, 2 resident CTAs per SM (64 registers): 32 copies up to 256 bins (lane-private words: conflict free), 16 at 512, 8 at 1024
     const int64_t nv = n / (16 / elem_bytes);
     int K = copies_env >= 200 ? copies_env - 200 : 32;
     while (K > 8 && nbins * K > 8192) K >>= 1;
     const int smem = nbins * K * 4;
     int64_t want_s = (nv + 511) / 512;
-    int grid_s = (int)(want_s < 1 ? 1 : want_s > (int64_t)num_sms() * 4 ? (int64_t)num_sms() * 4 : want_s);
+    static int hist_waves = -1;
+    if (hist_waves < 0) { const char* e = getenv("DDQST_HIST_CTAS_PER_SM"); hist_waves = e ? atoi(e) : 2; }     // = the resident CTAs (measured: 2 -> 3.85 TB/s, 4 -> 3.78, 8 -> 3.70)
+    int grid_s = (int)(want_s < 1 ? 1 : want_s > (int64_t)num_sms() * hist_waves ? (int64_t)num_sms() * hist_waves : want_s);
 #define DDQST_HIST_SHARED_LAUNCH(TT, KK)                                                                                                   \
     do {                                                                                                                                  \
       DDQST_CUDA_OK(cudaFuncSetAttribute(histogram_copies_kernel<TT, KK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
