@@ -392,7 +392,11 @@ int ddqst_sample_step(const ddqst_dims* d, const void* pack, const float* sched,
 
 // ------------------------------------------------------------------------------------ q_sample
 namespace ddqst {
-__global__ void q_sample_kernel(const float* __restrict__ Q, int T, int N, int cumulative,
+extern "C++" {
+// NBLK = ceil(N / 4) Philox blocks of qubit draws per sample, a compile-time count: the qubit loop unrolls, the word of a qubit is a
+// fixed lane of its block, and the two transition rows of Q[t] are read once as a float4
+template <int NBLK>
+__global__ void __launch_bounds__(256) q_sample_kernel(const float* __restrict__ Q, int T, int N, int cumulative,
                                 const uint16_t* __restrict__ x0, const int32_t* __restrict__ t_in, int64_t batch,
                                 int64_t row_offset, uint64_t seed, uint32_t stream_id,
                                 const int64_t* __restrict__ stream_dev, uint16_t* __restrict__ xt,
@@ -408,19 +412,44 @@ __global__ void q_sample_kernel(const float* __restrict__ Q, int T, int N, int c
     t = 1 + (int)(((uint64_t)(pt.x >> 8) * (uint64_t)T) >> 24);
   }
   if (t_out) t_out[i] = t;
-  const float* Qt = Q + (int64_t)t * 4;
-  uint32_t bits = x0[i], out = 0;
-  Philox4 p{};
-  for (int q = 0; q < N; ++q) {
-    if ((q & 3) == 0) p = stream_block(seed, stream_id, 0, DDQST_SITE_QSAMPLE, row, q >> 2);
-    uint32_t b = (bits >> q) & 1u;
-    float p0, p1;
-    if (cumulative) { p0 = Qt[b * 2 + 0]; p1 = Qt[b * 2 + 1]; }   // Q_bar[t][from=b][to]
-    else { p0 = Qt[0 * 2 + b]; p1 = Qt[1 * 2 + b]; }              // Q[t][to][from=b]
-    out |= draw_bit(word_to_uniform(lane_of(p, q)), p0, p1) << q;
+  const float4 qt = __ldg(reinterpret_cast<const float4*>(Q) + t);       // [a][b] row-major: x = [0][0], y = [0][1], z = [1][0], w = [1][1]
+  // from-bit 0 / 1: (p0, p1) = cumulative ? Q_bar[t][from][to 0 / 1] : Q[t][to 0 / 1][from]
+  const float p0_f0 = qt.x, p1_f0 = cumulative ? qt.y : qt.z;
+  const float p0_f1 = cumulative ? qt.z : qt.y, p1_f1 = qt.w;
+  const float s_f0 = __fadd_rn(p0_f0, p1_f0), s_f1 = __fadd_rn(p0_f1, p1_f1);
+  const uint32_t bits = x0[i];
+  uint32_t out = 0;
+#pragma unroll
+  for (int blk = 0; blk < NBLK; ++blk) {
+    if (blk * 4 < N) {
+      const Philox4 p = stream_block(seed, stream_id, 0, DDQST_SITE_QSAMPLE, row, blk);
+      const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = blk * 4 + j;
+        if (q < N) {
+          const bool from1 = (bits >> q) & 1u;
+          const float u = word_to_uniform(w[j]);
+          out |= (__fmul_rn(u, from1 ? s_f1 : s_f0) < (from1 ? p1_f1 : p1_f0) ? 1u : 0u) << q;     // draw_bit(u, p0, p1)
+        }
+      }
+    }
   }
   xt[i] = (uint16_t)out;
 }
+
+static void launch_q_sample(const float* Q, int T, int N, int cumulative, const uint16_t* x0, const int32_t* t_in, int64_t batch,
+                            int64_t row_offset, uint64_t seed, uint32_t stream_id, const int64_t* stream_dev, uint16_t* xt, int32_t* t_out,
+                            cudaStream_t s) {
+  const unsigned grid = (unsigned)((batch + 255) / 256);
+  switch ((N + 3) / 4) {
+    case 1: q_sample_kernel<1><<<grid, 256, 0, s>>>(Q, T, N, cumulative, x0, t_in, batch, row_offset, seed, stream_id, stream_dev, xt, t_out); break;
+    case 2: q_sample_kernel<2><<<grid, 256, 0, s>>>(Q, T, N, cumulative, x0, t_in, batch, row_offset, seed, stream_id, stream_dev, xt, t_out); break;
+    case 3: q_sample_kernel<3><<<grid, 256, 0, s>>>(Q, T, N, cumulative, x0, t_in, batch, row_offset, seed, stream_id, stream_dev, xt, t_out); break;
+    default: q_sample_kernel<4><<<grid, 256, 0, s>>>(Q, T, N, cumulative, x0, t_in, batch, row_offset, seed, stream_id, stream_dev, xt, t_out); break;
+  }
+}
+}  // extern "C++"
 
 __global__ void pack_bits_kernel(const int64_t* __restrict__ bits, int64_t batch, int N, uint16_t* __restrict__ packed) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -455,8 +484,9 @@ int ddqst_q_sample(const float* Q, int32_t num_timesteps, int32_t num_qubits, in
   DDQST_REQUIRE(num_qubits >= 1 && num_qubits <= 16 && num_timesteps >= 1 && batch >= 0, DDQST_EINVAL_SHAPE, "bad shape");
   if (batch == 0) return DDQST_OK;
   DDQST_REQUIRE(Q && x0_packed && xt_packed, DDQST_EINVAL_SHAPE, "NULL argument");
-  q_sample_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      Q, num_timesteps, num_qubits, cumulative, x0_packed, t, batch, row_offset, seed, stream_id, nullptr, xt_packed, t_out);
+  DDQST_REQUIRE(((uintptr_t)Q & 15) == 0, DDQST_EINVAL_SHAPE, "the transition table must be 16-byte aligned");
+  ddqst::launch_q_sample(Q, num_timesteps, num_qubits, cumulative, x0_packed, t, batch, row_offset, seed, stream_id, nullptr, xt_packed, t_out,
+                         (cudaStream_t)stream);
   DDQST_LAUNCH_OK();
   return DDQST_OK;
 }
@@ -468,8 +498,9 @@ int ddqst_q_sample_dev(const float* Q, int32_t num_timesteps, int32_t num_qubits
   DDQST_REQUIRE(num_qubits >= 1 && num_qubits <= 16 && num_timesteps >= 1 && batch >= 0, DDQST_EINVAL_SHAPE, "bad shape");
   if (batch == 0) return DDQST_OK;
   DDQST_REQUIRE(Q && x0_packed && xt_packed && stream_id_dev, DDQST_EINVAL_SHAPE, "NULL argument");
-  q_sample_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      Q, num_timesteps, num_qubits, cumulative, x0_packed, t, batch, row_offset, seed, 0u, stream_id_dev, xt_packed, t_out);
+  DDQST_REQUIRE(((uintptr_t)Q & 15) == 0, DDQST_EINVAL_SHAPE, "the transition table must be 16-byte aligned");
+  ddqst::launch_q_sample(Q, num_timesteps, num_qubits, cumulative, x0_packed, t, batch, row_offset, seed, 0u, stream_id_dev, xt_packed, t_out,
+                         (cudaStream_t)stream);
   DDQST_LAUNCH_OK();
   return DDQST_OK;
 }
