@@ -118,7 +118,7 @@ int ddqst_sample_step(const ddqst_dims* d, const void* pack, const float* sched,
 /* ---- D2 / D2': q_sample forward noising (RQC/diffusion.py:45-51, SS/diffusion.py:27-52).
  * Q[T+1,2,2]; cumulative=1 reads row x0 of Q_bar[t] ([from,to]); 0 reads column x0 of Q[t] ([to,from]).
  * If t == NULL the timesteps are drawn too: t = 1 + floor(u24*T) at site TSTEP (RQC/main.py:107) and
- * written to t_out (nullable).  * Q (the [T+1,2,2] transition table) must be 16-byte aligned. */
+ * written to t_out (nullable).  Q must be 16-byte aligned (each Q[t] is read as one float4). */
 int ddqst_q_sample(const float* Q, int32_t num_timesteps, int32_t num_qubits, int cumulative,
                    const uint16_t* x0_packed, const int32_t* t, int64_t batch, int64_t row_offset,
                    uint64_t seed, uint32_t stream_id, uint16_t* xt_packed, int32_t* t_out, void* stream);
