@@ -514,13 +514,30 @@ int ddqst_pack_bits(const int64_t* bits, int64_t batch, int32_t num_qubits, uint
   return DDQST_OK;
 }
 
+namespace ddqst {
+// N = 8, uint8 shots (the C4 shape): four threads per shot, each writing qubits 2j, 2j+1 of it as one 16-byte store -- a warp stores
+// 512 contiguous bytes per instruction, reads 8 bytes, and does no integer division
+__global__ void __launch_bounds__(256) unpack_bits8_kernel(const uint8_t* __restrict__ packed, int64_t batch, int64_t* __restrict__ bits) {
+  const int64_t th = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t shot = th >> 2;
+  if (shot >= batch) return;
+  const uint32_t v = packed[shot] >> (2 * (int)(th & 3));
+  *reinterpret_cast<longlong2*>(bits + 2 * th) = make_longlong2((long long)(v & 1u), (long long)((v >> 1) & 1u));
+}
+}  // namespace ddqst
+
 int ddqst_unpack_bits(const void* packed, int elem_bytes, int64_t batch, int32_t num_qubits, int64_t* bits, void* stream) {
   DDQST_TRY(check_arch());
   DDQST_REQUIRE(num_qubits >= 1 && num_qubits <= 16 && batch >= 0 && (elem_bytes == 1 || elem_bytes == 2), DDQST_EINVAL_SHAPE, "bad shape");
   if (batch == 0) return DDQST_OK;
   int64_t total = batch * num_qubits;
   DDQST_REQUIRE(((uintptr_t)bits & 15) == 0, DDQST_EINVAL_SHAPE, "bits must be 16-byte aligned");
-  unpack_bits_kernel<<<(unsigned)(((total + 1) / 2 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(packed, elem_bytes, total, num_qubits, bits);
+  static int fast8 = -1;
+  if (fast8 < 0) { const char* e = getenv("DDQST_UNPACK_FAST8"); fast8 = (e && e[0] == '0') ? 0 : 1; }
+  if (fast8 && num_qubits == 8 && elem_bytes == 1)
+    ddqst::unpack_bits8_kernel<<<(unsigned)((4 * batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)packed, batch, bits);
+  else
+    unpack_bits_kernel<<<(unsigned)(((total + 1) / 2 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(packed, elem_bytes, total, num_qubits, bits);
   DDQST_LAUNCH_OK();
   return DDQST_OK;
 }
