@@ -295,7 +295,10 @@ int ddqst_selftest_gemm_tc(const uint16_t* a, const uint16_t* b, int a_mn, int b
 int ddqst_selftest_gemm_tc_dbg(const uint16_t* a, const uint16_t* b, int a_mn, int b_mn, int32_t m, int32_t n, int32_t k,
                                int32_t batch, float* c, long long* dbg, void* stream);
 int ddqst_debug_tc_trace(long long* buf, int32_t cap);
-/* synchronises the device; returns the first pipeline-timeout code a tcgen05 kernel recorded (0 = none) */
+/* synchronises the device; returns the first pipeline-timeout code a kernel recorded (0 = none).  Every mbarrier / mailbox / grid-barrier
+ * wait in the tcgen05 kernels and in the eigensolver is bounded (~1 s); on a timeout the kernel drains with garbage instead of hanging
+ * and the first offender's code stays here: 1-49 sampler and training GEMM pipelines, 60-65 one-cluster Jacobi kernels, 66-70 line
+ * eigensolver (inbox, mailbox, sweep barrier), 71-73 block eigensolver (mailboxes, sweep barrier). */
 int ddqst_debug_tc_status(void);
 /* which forward + data-gradient implementation ddqst_train_forward_backward_tc uses: -1 = by batch size (default; the fused
  * persistent kernel of csrc/train_fused.cuh from 3072 rows, per-layer GEMM launches below), 0 = per-layer, 1 = fused. */
